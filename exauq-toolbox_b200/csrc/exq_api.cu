@@ -1,0 +1,983 @@
+// Host side of libexauq_b200.so: device state behind opaque handles, the recursive
+// potrf+trtri driver, chunked prediction / PEI pipeline and the C ABI of
+// include/exauq_b200.h.  sm_100a only; no CPU fallback.
+#include "../../include/exauq_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "exq_common.cuh"
+#include "gemm_dmma.cuh"
+#include "kernels.cuh"
+#include "leaf.cuh"
+
+using namespace exq;
+
+// -------------------------------------------------------------------------------------
+// global context
+// -------------------------------------------------------------------------------------
+namespace {
+
+struct ProfClass {
+    std::vector<std::pair<int, int>> pairs;   // indices into the event pool
+    int64_t launches = 0;
+    double flops = 0.0, bytes = 0.0;
+};
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    unsigned prof_mask = 0;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    ProfClass prof[EXQ_PROF_NCLASS];
+    bool attrs_set = false;
+} g;
+
+int fail(int code, const std::string& msg) {
+    g.err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return fail(EXQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+#define REQUIRE_READY()                                                               \
+    do {                                                                              \
+        if (!g.ready) return fail(EXQ_ERR_CUDA, "exq_init has not succeeded (no GPU?)"); \
+    } while (0)
+
+inline int pad128(int64_t n) { return (int)(((n + 127) / 128) * 128); }
+
+struct ProfMark {
+    int cls;
+    int e0 = -1;
+};
+
+ProfMark prof_begin(int cls, double flops, double bytes) {
+    ProfMark m{cls};
+    g.launches++;
+    g.prof[cls].launches++;
+    g.prof[cls].flops += flops;
+    g.prof[cls].bytes += bytes;
+    if (((g.prof_mask >> cls) & 1u) && g.pool_used + 2 <= g.pool.size()) {
+        m.e0 = (int)g.pool_used;
+        g.pool_used += 2;
+        cudaEventRecord(g.pool[m.e0], g.stream);
+    }
+    return m;
+}
+void prof_end(const ProfMark& m) {
+    if (m.e0 >= 0) {
+        cudaEventRecord(g.pool[m.e0 + 1], g.stream);
+        g.prof[m.cls].pairs.emplace_back(m.e0, m.e0 + 1);
+    }
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return EXQ_OK;
+}
+#define LAUNCH_CHECK(what)                     \
+    do {                                       \
+        int _rc = check_launch(what);          \
+        if (_rc != EXQ_OK) return _rc;         \
+    } while (0)
+
+int set_kernel_attrs() {
+    if (g.attrs_set) return EXQ_OK;
+    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_K, LAYOUT_K>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_K, LAYOUT_MN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_MN, LAYOUT_MN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  LEAF_SMEM_BYTES));
+    const int big = 220 * 1024;
+    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    g.attrs_set = true;
+    return EXQ_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// workspace for B same-sized systems
+// -------------------------------------------------------------------------------------
+struct Sys {
+    int B = 0, N = 0, Np = 0, d = 0;
+    double *A = nullptr, *Linv = nullptr, *W = nullptr;     // [B][Np][Np]
+    double* theta = nullptr;                                // [B][d+2]
+    double *tvec = nullptr, *alpha = nullptr, *dinv = nullptr, *kvec = nullptr;   // [B][Np]
+    double* ldq = nullptr;                                  // [B][2]
+    int* info = nullptr;                                    // [B]
+    double *Xb = nullptr, *yb = nullptr;                    // own data (LOO refits) or null
+    int* skip = nullptr;
+    double* gpartial = nullptr;                             // gradient partials
+    double* grad = nullptr;                                 // [B][d+2]
+    int64_t sq() const { return (int64_t)Np * Np; }
+};
+
+void sys_free(Sys& s) {
+    cudaFree(s.A); cudaFree(s.Linv); cudaFree(s.W); cudaFree(s.theta); cudaFree(s.tvec);
+    cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.ldq); cudaFree(s.info);
+    cudaFree(s.Xb); cudaFree(s.yb); cudaFree(s.skip); cudaFree(s.gpartial); cudaFree(s.grad);
+    s = Sys();
+}
+
+int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
+    if (s.B >= B && s.N == N && s.d == d && (!need_w || s.W) && (!own_data || s.Xb)) return EXQ_OK;
+    sys_free(s);
+    s.B = B; s.N = N; s.Np = pad128(N); s.d = d;
+    size_t mat = (size_t)B * s.sq() * sizeof(double);
+    CUDA_TRY(cudaMalloc(&s.A, mat));
+    CUDA_TRY(cudaMalloc(&s.Linv, mat));
+    if (need_w) CUDA_TRY(cudaMalloc(&s.W, mat));
+    CUDA_TRY(cudaMalloc(&s.theta, (size_t)B * (d + 2) * sizeof(double)));
+    size_t vec = (size_t)B * s.Np * sizeof(double);
+    CUDA_TRY(cudaMalloc(&s.tvec, vec));
+    CUDA_TRY(cudaMalloc(&s.alpha, vec));
+    CUDA_TRY(cudaMalloc(&s.dinv, vec));
+    CUDA_TRY(cudaMalloc(&s.kvec, vec));
+    CUDA_TRY(cudaMalloc(&s.ldq, (size_t)B * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&s.info, (size_t)B * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&s.grad, (size_t)B * (d + 2) * sizeof(double)));
+    if (need_w) {
+        int nt = s.Np / 128;
+        CUDA_TRY(cudaMalloc(&s.gpartial, (size_t)B * nt * nt * (64 + 2) * sizeof(double)));
+    }
+    if (own_data) {
+        CUDA_TRY(cudaMalloc(&s.Xb, (size_t)B * s.Np * d * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&s.yb, vec));
+        CUDA_TRY(cudaMalloc(&s.skip, (size_t)B * sizeof(int)));
+    }
+    return EXQ_OK;
+}
+
+}  // namespace
+
+struct exq_gp_s {
+    int64_t N = 0;
+    int d = 0, kernel_id = 0, Np = 0;
+    double *X = nullptr, *y = nullptr;     // [Np][d] zero padded, [Np]
+    Sys fit;                                // B = 1: fitted state
+    bool fitted = false;
+    double cov = 0.0, nugget = 0.0;
+    std::vector<double> corr_raw;
+    Sys batch;                              // MLE restarts / LOO refits
+    // prediction scratch
+    double *KcT = nullptr, *P = nullptr, *Xchunk = nullptr;
+    int64_t chunk = 0;
+    double* rep = nullptr;
+    int rep_cap = 0;
+};
+
+struct exq_cand_s {
+    int64_t M = 0, Mpad = 0;
+    int d = 0;
+    double *Xc = nullptr, *mean = nullptr, *var = nullptr, *pei = nullptr;
+    ArgPair *partial = nullptr, *best = nullptr, *chosen = nullptr;
+    double* xnew = nullptr;
+    int nblocks = 0, chosen_cap = 0;
+    bool evaluated = false;
+};
+
+namespace {
+
+// -------------------------------------------------------------------------------------
+// kernel launch helpers
+// -------------------------------------------------------------------------------------
+template <int AL, int BL>
+int launch_gemm(const GemmArgs& a, int batch, int cls) {
+    dim3 grid(a.N / GEMM_BN, a.M / GEMM_BM, batch);
+    // algorithmic flop estimate (triangular k ranges / lower-only halve the work)
+    double fl = 2.0 * a.M * (double)a.N * a.K * batch;
+    if (a.krange != KR_FULL) fl *= 0.5;
+    if (a.lower_only && a.krange == KR_FULL) fl *= 0.5;
+    if (a.lower_only && a.krange != KR_FULL) fl *= 2.0 / 3.0;
+    ProfMark m = prof_begin(cls, fl, 0.0);
+    gemm_dmma_kernel<AL, BL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(a);
+    prof_end(m);
+    return check_launch("gemm_dmma_kernel");
+}
+
+int launch_assemble(const AsmArgs& a, int rows_pad, int cols_pad, int batch) {
+    size_t smem = ((size_t)2 * 128 * a.d + (size_t)a.d * ASM_XT_LD + a.d + 2) * sizeof(double);
+    dim3 grid(cols_pad / 128, rows_pad / 128, batch);
+    double entries = (double)rows_pad * cols_pad * batch * (a.sym ? 0.5 : 1.0);
+    ProfMark m = prof_begin(EXQ_PROF_ASSEMBLE, entries * (3.0 * a.d + 30.0), entries * 8.0);
+    assemble_kernel<<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    prof_end(m);
+    return check_launch("assemble_kernel");
+}
+
+// fused recursive potrf + trtri on the diagonal block [r0, r0+n) of every system in s
+int factor_rec(Sys& s, int r0, int n) {
+    const int64_t ld = s.Np, sq = s.sq();
+    if (n == 128) {
+        ProfMark m = prof_begin(EXQ_PROF_LEAF, s.B * (128.0 * 128 * 128), 0.0);
+        leaf_potrf_trtri_kernel<<<s.B, LEAF_THREADS, LEAF_SMEM_BYTES, g.stream>>>(s.A, s.Linv, ld, sq, sq, r0,
+                                                                               s.info);
+        prof_end(m);
+        return check_launch("leaf_potrf_trtri_kernel");
+    }
+    const int nb = n / 128;
+    const int n1 = ((nb + 1) / 2) * 128, n2 = n - n1;
+    int rc = factor_rec(s, r0, n1);
+    if (rc) return rc;
+    double* A21 = s.A + (int64_t)(r0 + n1) * ld + r0;
+    double* A22 = s.A + (int64_t)(r0 + n1) * ld + (r0 + n1);
+    double* Li11 = s.Linv + (int64_t)r0 * ld + r0;
+    double* Li21 = s.Linv + (int64_t)(r0 + n1) * ld + r0;
+    double* Li22 = s.Linv + (int64_t)(r0 + n1) * ld + (r0 + n1);
+    GemmArgs a{};
+    a.lda = a.ldb = a.ldc = ld;
+    a.strideA = a.strideB = a.strideC = sq;
+    // (1) L21 := A21 * Linv11^T, parked in the Linv21 slot
+    a.A = A21; a.B = Li11; a.C = Li21; a.M = n2; a.N = n1; a.K = n1;
+    a.krange = KR_LE_J; a.lower_only = 0; a.cmode = C_STORE;
+    if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
+    // (2) A22 -= L21 * L21^T (lower tiles)
+    a.A = Li21; a.B = Li21; a.C = A22; a.M = n2; a.N = n2; a.K = n1;
+    a.krange = KR_FULL; a.lower_only = 1; a.cmode = C_SUB;
+    if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
+    if ((rc = factor_rec(s, r0 + n1, n2))) return rc;
+    // (3) T := L21 * Linv11, parked in the (now free) A21 slot
+    a.A = Li21; a.B = Li11; a.C = A21; a.M = n2; a.N = n1; a.K = n1;
+    a.krange = KR_GE_J; a.lower_only = 0; a.cmode = C_STORE;
+    if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
+    // (4) Linv21 := -Linv22 * T
+    a.A = Li22; a.B = A21; a.C = Li21; a.M = n2; a.N = n1; a.K = n2;
+    a.krange = KR_LE_I; a.lower_only = 0; a.cmode = C_NEG;
+    if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
+    return EXQ_OK;
+}
+
+// alpha = K^-1 y, dinv = diag K^-1, {logdet, quad}; y given per system with stride
+int solve_vectors(Sys& s, const double* y, int64_t strideY, int nvalid) {
+    const int64_t ld = s.Np, sq = s.sq();
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)s.B * s.Np * s.Np, (double)s.B * s.Np * s.Np * 4.0);
+    trmv_lower_kernel<<<dim3(s.Np / 8, 1, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, y, strideY, s.tvec, s.Np, s.Np);
+    prof_end(m);
+    LAUNCH_CHECK("trmv_lower_kernel");
+    m = prof_begin(EXQ_PROF_STREAM, 2.0 * s.B * s.Np * s.Np, (double)s.B * s.Np * s.Np * 4.0);
+    trmv_lower_t_kernel<<<dim3(s.Np / 32, 1, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, s.tvec, s.Np, s.alpha, s.dinv,
+                                                                      s.Np, s.Np);
+    prof_end(m);
+    LAUNCH_CHECK("trmv_lower_t_kernel");
+    m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+    logdet_quad_kernel<<<s.B, 256, 0, g.stream>>>(s.A, ld, sq, y, strideY, s.alpha, s.Np, nvalid, s.ldq);
+    prof_end(m);
+    LAUNCH_CHECK("logdet_quad_kernel");
+    return EXQ_OK;
+}
+
+// K^-1 (lower tiles) into s.W
+int lauum(Sys& s) {
+    GemmArgs a{};
+    a.lda = a.ldb = a.ldc = s.Np;
+    a.strideA = a.strideB = a.strideC = s.sq();
+    a.A = s.Linv; a.B = s.Linv; a.C = s.W; a.M = a.N = a.K = s.Np;
+    a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
+    return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
+}
+
+int assemble_sym(Sys& s, const double* X, int64_t strideX, int nvalid, int kernel_id) {
+    AsmArgs a{};
+    a.Xi = X; a.Xj = X; a.theta = s.theta; a.out = s.A;
+    a.ld = s.Np; a.strideOut = s.sq(); a.strideXi = strideX; a.strideXj = strideX; a.strideTheta = s.d + 2;
+    a.n_i = nvalid; a.n_j = nvalid; a.d = s.d; a.kernel_id = kernel_id; a.sym = 1; a.scale_sigma2 = 1;
+    return launch_assemble(a, s.Np, s.Np, s.B);
+}
+
+int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
+    if (gp->chunk >= want_chunk) return EXQ_OK;
+    cudaFree(gp->KcT); cudaFree(gp->P); cudaFree(gp->Xchunk);
+    gp->KcT = gp->P = gp->Xchunk = nullptr;
+    gp->chunk = 0;
+    CUDA_TRY(cudaMalloc(&gp->KcT, (size_t)want_chunk * gp->Np * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&gp->P, (size_t)(gp->Np / 128) * want_chunk * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&gp->Xchunk, (size_t)want_chunk * gp->d * sizeof(double)));
+    gp->chunk = want_chunk;
+    return EXQ_OK;
+}
+
+int64_t default_chunk(const exq_gp_t gp, int64_t Mpad) {
+    // keep the KcT chunk around 1 GiB and at least a few waves of tiles
+    int64_t c = ((int64_t)1 << 27) / gp->Np;
+    c = std::max<int64_t>(128, (c / 128) * 128);
+    c = std::min<int64_t>(c, 32768);
+    return std::min(c, Mpad);
+}
+
+// mean / var / (pei) of the fitted GP at device-resident candidates Xc[Mpad][d]
+int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const double* rep, int n_rep,
+                   double tmax, int want_pei, double* mean, double* var, double* pei) {
+    const int Np = gp->Np;
+    int64_t chunk = default_chunk(gp, Mpad);
+    int rc = ensure_pred_scratch(gp, chunk);
+    if (rc) return rc;
+    chunk = std::min<int64_t>(gp->chunk, Mpad);
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int64_t mc_pad = std::min(chunk, Mpad - c0);
+        const int64_t mc = std::min(mc_pad, M - c0);
+        AsmArgs a{};
+        a.Xi = Xc + c0 * gp->d; a.Xj = gp->X; a.theta = gp->fit.theta; a.out = gp->KcT;
+        a.ld = Np; a.n_i = (int)mc; a.n_j = (int)gp->N; a.d = gp->d; a.kernel_id = gp->kernel_id;
+        a.sym = 0; a.scale_sigma2 = 1;
+        if ((rc = launch_assemble(a, (int)mc_pad, Np, 1))) return rc;
+        GemmArgs ga{};
+        ga.A = gp->fit.Linv; ga.B = gp->KcT; ga.C = gp->P;
+        ga.lda = Np; ga.ldb = Np; ga.ldc = mc_pad;
+        ga.M = Np; ga.N = (int)mc_pad; ga.K = Np;
+        ga.krange = KR_LE_I; ga.lower_only = 0; ga.cmode = C_COLSUMSQ;
+        if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
+        FinArgs f{};
+        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = Np / 128;
+        f.alpha = gp->fit.alpha; f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep;
+        f.N = (int)gp->N; f.Np = Np; f.d = gp->d; f.kernel_id = gp->kernel_id; f.m_valid = (int)mc;
+        f.tmax = tmax; f.want_pei = want_pei;
+        f.mean = mean ? mean + c0 : nullptr; f.var = var ? var + c0 : nullptr; f.pei = pei ? pei + c0 : nullptr;
+        ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)mc * gp->N * 4.0, (double)mc * Np * 8.0);
+        predict_finalize_kernel<<<(unsigned)((mc + 7) / 8), 256, 0, g.stream>>>(f);
+        prof_end(m);
+        LAUNCH_CHECK("predict_finalize_kernel");
+    }
+    return EXQ_OK;
+}
+
+int upload_theta(Sys& s, const std::vector<double>& host) {
+    CUDA_TRY(cudaMemcpyAsync(s.theta, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    return EXQ_OK;
+}
+
+// one assemble + factor pass over the first `B` systems of s; returns info on the host
+int assemble_and_factor(Sys& s, const double* X, int64_t strideX, int nvalid, int kernel_id,
+                        std::vector<int>& info_host) {
+    int rc;
+    CUDA_TRY(cudaMemsetAsync(s.info, 0, s.B * sizeof(int), g.stream));
+    if ((rc = assemble_sym(s, X, strideX, nvalid, kernel_id))) return rc;
+    if ((rc = factor_rec(s, 0, s.Np))) return rc;
+    info_host.resize(s.B);
+    CUDA_TRY(cudaMemcpyAsync(info_host.data(), s.info, s.B * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return EXQ_OK;
+}
+
+int pei_argmax_launch(exq_gp_t gp, exq_cand_t c, const double* xnew_dev) {
+    size_t smem = 2 * c->d * sizeof(double);
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)c->M * (3.0 * c->d + 35.0),
+                            xnew_dev ? (double)c->M * (c->d + 2) * 8.0 : (double)c->M * 8.0);
+    pei_update_argmax_kernel<<<c->nblocks, 256, smem, g.stream>>>(c->pei, c->Xc, c->M, c->d, gp ? gp->kernel_id : 0,
+                                                                  gp ? gp->fit.theta : nullptr, xnew_dev, c->partial);
+    prof_end(m);
+    LAUNCH_CHECK("pei_update_argmax_kernel");
+    m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+    argmax_final_kernel<<<1, 256, 0, g.stream>>>(c->partial, c->nblocks, c->best);
+    prof_end(m);
+    LAUNCH_CHECK("argmax_final_kernel");
+    return EXQ_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char* exq_last_error(void) { return g.err.c_str(); }
+
+int exq_init(int device) {
+    if (g.ready && g.device == device) return EXQ_OK;
+    if (g.ready) return fail(EXQ_ERR_STATE, "already initialised on another device");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(EXQ_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(EXQ_ERR_ARG, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(EXQ_ERR_CUDA, "libexauq_b200 is built for sm_100a only; found sm_" +
+                                      std::to_string(prop.major) + std::to_string(prop.minor));
+    g.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&g.t0));
+    CUDA_TRY(cudaEventCreate(&g.t1));
+    g.device = device;
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    g.ready = true;
+    return EXQ_OK;
+}
+
+int exq_shutdown(void) {
+    if (!g.ready) return EXQ_OK;
+    cudaStreamSynchronize(g.stream);
+    for (auto ev : g.pool) cudaEventDestroy(ev);
+    g.pool.clear();
+    cudaEventDestroy(g.t0);
+    cudaEventDestroy(g.t1);
+    cudaStreamDestroy(g.stream);
+    g = Ctx();
+    return EXQ_OK;
+}
+
+int exq_device_sm_count(void) { return g.sm_count; }
+int64_t exq_launch_count(void) { return g.launches; }
+
+int exq_timer_start(void) {
+    REQUIRE_READY();
+    CUDA_TRY(cudaEventRecord(g.t0, g.stream));
+    return EXQ_OK;
+}
+int exq_timer_stop(double* ms) {
+    REQUIRE_READY();
+    CUDA_TRY(cudaEventRecord(g.t1, g.stream));
+    CUDA_TRY(cudaEventSynchronize(g.t1));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, g.t0, g.t1));
+    if (ms) *ms = f;
+    return EXQ_OK;
+}
+
+int exq_prof_enable(int mask) {
+    REQUIRE_READY();
+    if (mask && g.pool.empty()) {
+        g.pool.resize(16384);
+        for (auto& ev : g.pool) CUDA_TRY(cudaEventCreate(&ev));
+    }
+    g.prof_mask = (unsigned)mask;
+    return EXQ_OK;
+}
+int exq_prof_reset(void) {
+    REQUIRE_READY();
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    g.pool_used = 0;
+    for (auto& p : g.prof) p = ProfClass();
+    return EXQ_OK;
+}
+int exq_prof_get(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes) {
+    REQUIRE_READY();
+    if (cls < 0 || cls >= EXQ_PROF_NCLASS) return fail(EXQ_ERR_ARG, "bad profile class");
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    double tot = 0.0;
+    for (auto& pr : g.prof[cls].pairs) {
+        float f = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&f, g.pool[pr.first], g.pool[pr.second]));
+        tot += f;
+    }
+    // scale up if the event pool ran out before every launch could be timed
+    size_t timed = g.prof[cls].pairs.size();
+    if (timed > 0 && (int64_t)timed < g.prof[cls].launches) tot *= (double)g.prof[cls].launches / (double)timed;
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = g.prof[cls].launches;
+    if (flops) *flops = g.prof[cls].flops;
+    if (bytes) *bytes = g.prof[cls].bytes;
+    return EXQ_OK;
+}
+
+// ---- correlation ------------------------------------------------------------------------
+int exq_corr(int kernel_id, int d, const double* corr_raw, const double* A, int64_t n1, const double* B,
+             int64_t n2, double* out) {
+    REQUIRE_READY();
+    if (d < 1 || d > EXQ_MAX_D || n1 < 1 || n2 < 1 || !corr_raw || !A || !B || !out)
+        return fail(EXQ_ERR_ARG, "exq_corr: bad argument");
+    if (kernel_id < 0 || kernel_id > 2) return fail(EXQ_ERR_ARG, "exq_corr: bad kernel id");
+    const int p1 = pad128(n1), p2 = pad128(n2);
+    double *dA = nullptr, *dB = nullptr, *dT = nullptr, *dO = nullptr;
+    std::vector<double> th(d + 2);
+    for (int k = 0; k < d; k++) th[k] = exp(corr_raw[k]);
+    th[d] = 1.0; th[d + 1] = 0.0;
+    int rc = EXQ_OK;
+    auto cleanup = [&]() { cudaFree(dA); cudaFree(dB); cudaFree(dT); cudaFree(dO); };
+#define CORR_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            cleanup();                                                                   \
+            return fail(EXQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                \
+    } while (0)
+    CORR_TRY(cudaMalloc(&dA, (size_t)p1 * d * sizeof(double)));
+    CORR_TRY(cudaMalloc(&dB, (size_t)p2 * d * sizeof(double)));
+    CORR_TRY(cudaMalloc(&dT, (d + 2) * sizeof(double)));
+    CORR_TRY(cudaMalloc(&dO, (size_t)p1 * p2 * sizeof(double)));
+    CORR_TRY(cudaMemsetAsync(dA, 0, (size_t)p1 * d * sizeof(double), g.stream));
+    CORR_TRY(cudaMemsetAsync(dB, 0, (size_t)p2 * d * sizeof(double), g.stream));
+    CORR_TRY(cudaMemcpyAsync(dA, A, (size_t)n1 * d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CORR_TRY(cudaMemcpyAsync(dB, B, (size_t)n2 * d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CORR_TRY(cudaMemcpyAsync(dT, th.data(), (d + 2) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    AsmArgs a{};
+    a.Xi = dA; a.Xj = dB; a.theta = dT; a.out = dO; a.ld = p2;
+    a.n_i = (int)n1; a.n_j = (int)n2; a.d = d; a.kernel_id = kernel_id; a.sym = 0; a.scale_sigma2 = 0;
+    rc = launch_assemble(a, p1, p2, 1);
+    if (rc) { cleanup(); return rc; }
+    CORR_TRY(cudaMemcpy2DAsync(out, (size_t)n2 * sizeof(double), dO, (size_t)p2 * sizeof(double),
+                               (size_t)n2 * sizeof(double), (size_t)n1, cudaMemcpyDeviceToHost, g.stream));
+    CORR_TRY(cudaStreamSynchronize(g.stream));
+    cleanup();
+#undef CORR_TRY
+    return EXQ_OK;
+}
+
+// ---- GP handle ----------------------------------------------------------------------------
+int exq_gp_create(int64_t N, int d, const double* X, const double* y, int kernel_id, exq_gp_t* out) {
+    REQUIRE_READY();
+    if (N < 1 || d < 1 || d > EXQ_MAX_D || !X || !y || !out) return fail(EXQ_ERR_ARG, "exq_gp_create: bad argument");
+    if (kernel_id < 0 || kernel_id > 2) return fail(EXQ_ERR_ARG, "exq_gp_create: bad kernel id");
+    if (N > 65536) return fail(EXQ_ERR_ARG, "exq_gp_create: N too large");
+    exq_gp_t gp = new exq_gp_s();
+    gp->N = N; gp->d = d; gp->kernel_id = kernel_id; gp->Np = pad128(N);
+    cudaError_t e;
+    if ((e = cudaMalloc(&gp->X, (size_t)gp->Np * d * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&gp->y, (size_t)gp->Np * sizeof(double))) != cudaSuccess) {
+        exq_gp_destroy(gp);
+        return fail(EXQ_ERR_CUDA, std::string("exq_gp_create: ") + cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(gp->X, 0, (size_t)gp->Np * d * sizeof(double), g.stream);
+    cudaMemsetAsync(gp->y, 0, (size_t)gp->Np * sizeof(double), g.stream);
+    cudaMemcpyAsync(gp->X, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    cudaMemcpyAsync(gp->y, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) {
+        exq_gp_destroy(gp);
+        return fail(EXQ_ERR_CUDA, std::string("exq_gp_create: ") + cudaGetErrorString(e));
+    }
+    *out = gp;
+    return EXQ_OK;
+}
+
+int exq_gp_destroy(exq_gp_t gp) {
+    if (!gp) return EXQ_OK;
+    if (g.ready) cudaStreamSynchronize(g.stream);
+    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->KcT); cudaFree(gp->P); cudaFree(gp->Xchunk); cudaFree(gp->rep);
+    sys_free(gp->fit);
+    sys_free(gp->batch);
+    delete gp;
+    return EXQ_OK;
+}
+
+int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, int nugget_mode,
+               double* nugget_used, double* logdet, double* quad) {
+    REQUIRE_READY();
+    if (!gp || !corr_raw || !(cov > 0.0) || nugget < 0.0) return fail(EXQ_ERR_ARG, "exq_gp_fit: bad argument");
+    const int d = gp->d;
+    int rc = sys_alloc(gp->fit, 1, (int)gp->N, d, false, false);
+    if (rc) return rc;
+    gp->fitted = false;
+    std::vector<double> th(d + 2);
+    for (int k = 0; k < d; k++) {
+        th[k] = exp(corr_raw[k]);
+        if (!isfinite(th[k])) return fail(EXQ_ERR_ARG, "exq_gp_fit: overflow in exp(corr_raw)");
+    }
+    th[d] = cov;
+    double nug = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 0.0 : nugget;
+    std::vector<int> info;
+    const int max_tries = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 6 : 1;
+    bool ok = false;
+    for (int attempt = 0; attempt < max_tries; attempt++) {
+        th[d + 1] = nug;
+        if ((rc = upload_theta(gp->fit, th))) return rc;
+        if ((rc = assemble_and_factor(gp->fit, gp->X, 0, (int)gp->N, gp->kernel_id, info))) return rc;
+        if (info[0] == 0) { ok = true; break; }
+        nug = (attempt == 0) ? cov * 1e-6 : nug * 10.0;   // mogp jit_cholesky
+    }
+    if (!ok) return fail(EXQ_NOT_PD, "covariance matrix is not positive definite");
+    if ((rc = solve_vectors(gp->fit, gp->y, 0, (int)gp->N))) return rc;
+    double ldq[2];
+    CUDA_TRY(cudaMemcpyAsync(ldq, gp->fit.ldq, sizeof(ldq), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    gp->fitted = true;
+    gp->cov = cov;
+    gp->nugget = nug;
+    gp->corr_raw.assign(corr_raw, corr_raw + d);
+    if (nugget_used) *nugget_used = nug;
+    if (logdet) *logdet = ldq[0];
+    if (quad) *quad = ldq[1];
+    return EXQ_OK;
+}
+
+int exq_gp_predict(exq_gp_t gp, const double* Xc, int64_t M, double* mean, double* var) {
+    REQUIRE_READY();
+    if (!gp || !Xc || M < 1) return fail(EXQ_ERR_ARG, "exq_gp_predict: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_predict: GP has not been fitted");
+    exq_cand_t c = nullptr;
+    int rc = exq_cand_create(M, gp->d, Xc, &c);
+    if (rc) return rc;
+    rc = predict_device(gp, c->Xc, M, c->Mpad, nullptr, 0, 0.0, 0, c->mean, c->var, nullptr);
+    if (!rc && mean) rc = exq_cand_download(c, 0, mean);
+    if (!rc && var) rc = exq_cand_download(c, 1, var);
+    exq_cand_destroy(c);
+    return rc;
+}
+
+int exq_gp_loo(exq_gp_t gp, double* mean, double* var, double* nes) {
+    REQUIRE_READY();
+    if (!gp) return fail(EXQ_ERR_ARG, "exq_gp_loo: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_loo: GP has not been fitted");
+    const int N = (int)gp->N;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)3 * N * sizeof(double)));
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, 20.0 * N, 48.0 * N);
+    loo_kernel<<<(N + 255) / 256, 256, 0, g.stream>>>(gp->y, gp->fit.alpha, gp->fit.dinv, N, out, out + N, out + 2 * N);
+    prof_end(m);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && mean) e = cudaMemcpyAsync(mean, out, N * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess && var) e = cudaMemcpyAsync(var, out + N, N * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess && nes) e = cudaMemcpyAsync(nes, out + 2 * N, N * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string("exq_gp_loo: ") + cudaGetErrorString(e));
+    return EXQ_OK;
+}
+
+int exq_gp_loo_refit(exq_gp_t gp, const int* idx, int cnt, double* mean, double* var, double* nes) {
+    REQUIRE_READY();
+    if (!gp || !idx || cnt < 1) return fail(EXQ_ERR_ARG, "exq_gp_loo_refit: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_loo_refit: GP has not been fitted");
+    if (gp->N < 2) return fail(EXQ_ERR_ARG, "exq_gp_loo_refit: need at least 2 training points");
+    for (int i = 0; i < cnt; i++)
+        if (idx[i] < 0 || idx[i] >= gp->N) return fail(EXQ_ERR_ARG, "exq_gp_loo_refit: index out of range");
+    const int Nm = (int)gp->N - 1, d = gp->d;
+    const int Npm = pad128(Nm);
+    // systems per pass: bounded by ~24 GiB of matrices
+    int64_t per = (int64_t)2 * Npm * Npm * 8;
+    int Bmax = (int)std::max<int64_t>(1, std::min<int64_t>(64, ((int64_t)24 << 30) / per));
+    Bmax = std::min(Bmax, cnt);
+    int rc = sys_alloc(gp->batch, Bmax, Nm, d, false, true);
+    if (rc) return rc;
+    Sys& s = gp->batch;
+    std::vector<double> th(d + 2);
+    for (int k = 0; k < d; k++) th[k] = exp(gp->corr_raw[k]);
+    th[d] = gp->cov; th[d + 1] = gp->nugget;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)3 * Bmax * sizeof(double)));
+    for (int b0 = 0; b0 < cnt; b0 += Bmax) {
+        const int B = std::min(Bmax, cnt - b0);
+        const int Bsave = s.B;
+        s.B = B;
+        std::vector<double> thb((size_t)B * (d + 2));
+        for (int b = 0; b < B; b++) std::copy(th.begin(), th.end(), thb.begin() + (size_t)b * (d + 2));
+        cudaMemcpyAsync(s.theta, thb.data(), thb.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+        cudaMemcpyAsync(s.skip, idx + b0, B * sizeof(int), cudaMemcpyHostToDevice, g.stream);
+        ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)B * Npm * (d + 1) * 16.0);
+        gather_skip_kernel<<<dim3((Npm + 255) / 256, B), 256, 0, g.stream>>>(gp->X, gp->y, (int)gp->N, d, s.skip, s.Xb,
+                                                                          (int64_t)s.Np * d, s.yb, s.Np, s.Np);
+        prof_end(m);
+        std::vector<int> info;
+        rc = check_launch("gather_skip_kernel");
+        if (!rc) rc = assemble_and_factor(s, s.Xb, (int64_t)s.Np * d, Nm, gp->kernel_id, info);
+        if (!rc)
+            for (int b = 0; b < B; b++)
+                if (info[b] != 0) rc = fail(EXQ_NOT_PD, "LOO system not positive definite");
+        if (!rc) rc = solve_vectors(s, s.yb, s.Np, Nm);
+        if (!rc) {
+            m = prof_begin(EXQ_PROF_STREAM, (double)B * Nm * (3.0 * d + 30.0), (double)B * Nm * d * 8.0);
+            loo_cross_vec_kernel<<<dim3((Npm + 255) / 256, B), 256, 0, g.stream>>>(
+                gp->X, s.Xb, (int64_t)s.Np * d, s.skip, s.theta, d + 2, (int)gp->N, d, gp->kernel_id, s.kvec, s.Np, s.Np);
+            prof_end(m);
+            rc = check_launch("loo_cross_vec_kernel");
+        }
+        if (!rc) {
+            m = prof_begin(EXQ_PROF_STREAM, (double)B * s.Np * s.Np, (double)B * s.Np * s.Np * 4.0);
+            trmv_lower_kernel<<<dim3(s.Np / 8, 1, B), 256, 0, g.stream>>>(s.Linv, s.Np, s.sq(), s.kvec, s.Np, s.tvec, s.Np,
+                                                                       s.Np);
+            prof_end(m);
+            rc = check_launch("trmv_lower_kernel");
+        }
+        if (!rc) {
+            m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+            loo_refit_finish_kernel<<<B, 256, 0, g.stream>>>(s.kvec, s.tvec, s.alpha, s.Np, s.theta, d + 2, d, gp->y, s.skip,
+                                                           s.Np, out, out + Bmax, out + 2 * Bmax);
+            prof_end(m);
+            rc = check_launch("loo_refit_finish_kernel");
+        }
+        cudaError_t e = cudaSuccess;
+        if (!rc && mean) e = cudaMemcpyAsync(mean + b0, out, B * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+        if (!rc && e == cudaSuccess && var) e = cudaMemcpyAsync(var + b0, out + Bmax, B * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+        if (!rc && e == cudaSuccess && nes) e = cudaMemcpyAsync(nes + b0, out + 2 * Bmax, B * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        s.B = Bsave;
+        if (!rc && e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_loo_refit: ") + cudaGetErrorString(e));
+        if (rc) break;
+    }
+    cudaFree(out);
+    return rc;
+}
+
+int exq_gp_kinv(exq_gp_t gp, double* out) {
+    REQUIRE_READY();
+    if (!gp || !out) return fail(EXQ_ERR_ARG, "exq_gp_kinv: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_kinv: GP has not been fitted");
+    const int N = (int)gp->N, d = gp->d;
+    Sys tmp;
+    int rc = sys_alloc(tmp, 1, N, d, true, false);
+    if (rc) { sys_free(tmp); return rc; }
+    std::vector<double> th(d + 2);
+    for (int k = 0; k < d; k++) th[k] = exp(gp->corr_raw[k]);
+    th[d] = gp->cov; th[d + 1] = 0.0;
+    std::vector<int> info;
+    rc = upload_theta(tmp, th);
+    if (!rc) rc = assemble_and_factor(tmp, gp->X, 0, N, gp->kernel_id, info);
+    if (!rc && info[0] != 0) rc = fail(EXQ_NOT_PD, "Covariance Matrix is, or too close to singular.");
+    if (!rc) rc = lauum(tmp);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy2DAsync(out, (size_t)N * sizeof(double), tmp.W, (size_t)tmp.Np * sizeof(double),
+                                          (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, g.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_kinv: ") + cudaGetErrorString(e));
+    }
+    sys_free(tmp);
+    if (rc) return rc;
+    for (int i = 0; i < N; i++)   // mirror the lower triangle
+        for (int j = i + 1; j < N; j++) out[(size_t)i * N + j] = out[(size_t)j * N + i];
+    return EXQ_OK;
+}
+
+int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nugget, int nugget_mode,
+                         double* val, double* grad, int* info_out, double* nugget_used) {
+    REQUIRE_READY();
+    if (!gp || R < 1 || !theta_raw || !val) return fail(EXQ_ERR_ARG, "exq_gp_logpost_batch: bad argument");
+    const int N = (int)gp->N, d = gp->d, Np = gp->Np;
+    int64_t per = (int64_t)3 * Np * Np * 8;
+    int Bmax = (int)std::max<int64_t>(1, std::min<int64_t>(128, ((int64_t)96 << 30) / per));
+    Bmax = std::min(Bmax, R);
+    int rc = sys_alloc(gp->batch, Bmax, N, d, true, false);
+    if (rc) return rc;
+    Sys& s = gp->batch;
+    const int dmax = d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
+    const int nt = Np / 128;
+    const double ln2pi = 1.8378770664093453;
+    for (int b0 = 0; b0 < R; b0 += Bmax) {
+        const int B = std::min(Bmax, R - b0);
+        const int Bsave = s.B;
+        s.B = B;
+        std::vector<double> thb((size_t)B * (d + 2));
+        std::vector<double> nug(B, nugget_mode == EXQ_NUGGET_ADAPTIVE ? 0.0 : nugget);
+        std::vector<int> bad(B, 0);
+        for (int b = 0; b < B; b++) {
+            const double* raw = theta_raw + (size_t)(b0 + b) * (d + 1);
+            for (int k = 0; k < d; k++) {
+                thb[(size_t)b * (d + 2) + k] = exp(raw[k]);
+                if (!isfinite(thb[(size_t)b * (d + 2) + k])) bad[b] = 1;
+            }
+            double cv = exp(raw[d]);
+            if (!isfinite(cv) || !(cv > 0.0)) bad[b] = 1;
+            if (bad[b]) {   // keep the kernels well defined; the result is flagged
+                for (int k = 0; k < d; k++) thb[(size_t)b * (d + 2) + k] = 1.0;
+                cv = 1.0;
+            }
+            thb[(size_t)b * (d + 2) + d] = cv;
+            thb[(size_t)b * (d + 2) + d + 1] = nug[b];
+        }
+        std::vector<int> info;
+        const int max_tries = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 6 : 1;
+        for (int attempt = 0; attempt < max_tries; attempt++) {
+            cudaMemcpyAsync(s.theta, thb.data(), thb.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+            rc = assemble_and_factor(s, gp->X, 0, N, gp->kernel_id, info);
+            if (rc) break;
+            bool any = false;
+            for (int b = 0; b < B; b++) {
+                if (info[b] != 0 && attempt + 1 < max_tries) {
+                    double cv = thb[(size_t)b * (d + 2) + d];
+                    nug[b] = (nug[b] == 0.0) ? cv * 1e-6 : nug[b] * 10.0;
+                    thb[(size_t)b * (d + 2) + d + 1] = nug[b];
+                    any = true;
+                }
+            }
+            if (!any) break;
+            // adaptive retry: systems that succeeded are refactored with unchanged theta
+        }
+        if (!rc) rc = solve_vectors(s, gp->y, 0, N);
+        if (!rc && grad) rc = lauum(s);
+        if (!rc && grad) {
+            size_t smem = ((size_t)128 * d + (size_t)d * ASM_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
+            dim3 grid(nt, nt, B);
+            ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)B * N * N * 0.5 * (5.0 * d + 40.0), (double)B * N * N * 4.0);
+            if (dmax == 8)
+                grad_kernel<8><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d,
+                                                           gp->kernel_id, s.gpartial, nt);
+            else if (dmax == 16)
+                grad_kernel<16><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d,
+                                                            gp->kernel_id, s.gpartial, nt);
+            else if (dmax == 32)
+                grad_kernel<32><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d,
+                                                            gp->kernel_id, s.gpartial, nt);
+            else
+                grad_kernel<64><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d,
+                                                            gp->kernel_id, s.gpartial, nt);
+            prof_end(m);
+            rc = check_launch("grad_kernel");
+            if (!rc) {
+                m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+                grad_reduce_kernel<<<B, 128, 0, g.stream>>>(s.gpartial, nt, dmax, d, s.grad);
+                prof_end(m);
+                rc = check_launch("grad_reduce_kernel");
+            }
+        }
+        std::vector<double> ldq((size_t)B * 2), gh((size_t)B * (d + 2));
+        if (!rc) {
+            cudaMemcpyAsync(ldq.data(), s.ldq, ldq.size() * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+            if (grad) cudaMemcpyAsync(gh.data(), s.grad, gh.size() * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+            cudaError_t e = cudaStreamSynchronize(g.stream);
+            if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_logpost_batch: ") + cudaGetErrorString(e));
+        }
+        s.B = Bsave;
+        if (rc) return rc;
+        for (int b = 0; b < B; b++) {
+            const bool failed = bad[b] || info[b] != 0;
+            val[b0 + b] = failed ? NAN : 0.5 * (ldq[2 * b] + ldq[2 * b + 1] + N * ln2pi);
+            if (grad)
+                for (int k = 0; k < d + 1; k++) grad[(size_t)(b0 + b) * (d + 1) + k] = failed ? NAN : gh[(size_t)b * (d + 2) + k];
+            if (info_out) info_out[b0 + b] = failed ? EXQ_NOT_PD : 0;
+            if (nugget_used) nugget_used[b0 + b] = nug[b];
+        }
+    }
+    return EXQ_OK;
+}
+
+// ---- candidates ---------------------------------------------------------------------------
+int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out) {
+    REQUIRE_READY();
+    if (M < 1 || d < 1 || d > EXQ_MAX_D || !Xc || !out) return fail(EXQ_ERR_ARG, "exq_cand_create: bad argument");
+    exq_cand_t c = new exq_cand_s();
+    c->M = M; c->d = d; c->Mpad = ((M + 127) / 128) * 128;
+    c->nblocks = (int)std::min<int64_t>((M + 255) / 256, 4 * std::max(1, g.sm_count));
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void**)&c->Xc, (size_t)c->Mpad * d * sizeof(double));
+    A((void**)&c->mean, (size_t)c->Mpad * sizeof(double));
+    A((void**)&c->var, (size_t)c->Mpad * sizeof(double));
+    A((void**)&c->pei, (size_t)c->Mpad * sizeof(double));
+    A((void**)&c->partial, (size_t)c->nblocks * sizeof(ArgPair));
+    A((void**)&c->best, sizeof(ArgPair));
+    A((void**)&c->xnew, (size_t)d * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->Xc, 0, (size_t)c->Mpad * d * sizeof(double), g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->Xc, Xc, (size_t)M * d * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) {
+        exq_cand_destroy(c);
+        return fail(EXQ_ERR_CUDA, std::string("exq_cand_create: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return EXQ_OK;
+}
+
+int exq_cand_destroy(exq_cand_t c) {
+    if (!c) return EXQ_OK;
+    if (g.ready) cudaStreamSynchronize(g.stream);
+    cudaFree(c->Xc); cudaFree(c->mean); cudaFree(c->var); cudaFree(c->pei);
+    cudaFree(c->partial); cudaFree(c->best); cudaFree(c->chosen); cudaFree(c->xnew);
+    delete c;
+    return EXQ_OK;
+}
+
+int exq_pei_eval(exq_gp_t gp, exq_cand_t c, const double* rep, int n_rep, double tmax) {
+    REQUIRE_READY();
+    if (!gp || !c || n_rep < 0 || (n_rep > 0 && !rep)) return fail(EXQ_ERR_ARG, "exq_pei_eval: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_pei_eval: GP has not been fitted");
+    if (c->d != gp->d) return fail(EXQ_ERR_ARG, "exq_pei_eval: dimension mismatch");
+    if (n_rep > gp->rep_cap) {
+        cudaFree(gp->rep);
+        gp->rep = nullptr;
+        gp->rep_cap = 0;
+        CUDA_TRY(cudaMalloc(&gp->rep, (size_t)n_rep * gp->d * sizeof(double)));
+        gp->rep_cap = n_rep;
+    }
+    if (n_rep > 0)
+        CUDA_TRY(cudaMemcpyAsync(gp->rep, rep, (size_t)n_rep * gp->d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    int rc = predict_device(gp, c->Xc, c->M, c->Mpad, gp->rep, n_rep, tmax, 1, c->mean, c->var, c->pei);
+    if (rc) return rc;
+    rc = pei_argmax_launch(gp, c, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    c->evaluated = true;
+    return EXQ_OK;
+}
+
+int exq_pei_argmax(exq_cand_t c, int64_t* idx, double* val) {
+    REQUIRE_READY();
+    if (!c) return fail(EXQ_ERR_ARG, "exq_pei_argmax: bad argument");
+    if (!c->evaluated) return fail(EXQ_ERR_STATE, "exq_pei_argmax: call exq_pei_eval first");
+    ArgPair h;
+    CUDA_TRY(cudaMemcpyAsync(&h, c->best, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    if (idx) *idx = h.i;
+    if (val) *val = h.v;
+    return EXQ_OK;
+}
+
+int exq_pei_add_point(exq_gp_t gp, exq_cand_t c, const double* x) {
+    REQUIRE_READY();
+    if (!gp || !c || !x) return fail(EXQ_ERR_ARG, "exq_pei_add_point: bad argument");
+    if (!c->evaluated) return fail(EXQ_ERR_STATE, "exq_pei_add_point: call exq_pei_eval first");
+    CUDA_TRY(cudaMemcpyAsync(c->xnew, x, c->d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    int rc = pei_argmax_launch(gp, c, c->xnew);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return EXQ_OK;
+}
+
+int exq_pei_batch(exq_gp_t gp, exq_cand_t c, int batch_size, int64_t* idx, double* val) {
+    REQUIRE_READY();
+    if (!gp || !c || batch_size < 1) return fail(EXQ_ERR_ARG, "exq_pei_batch: bad argument");
+    if (!c->evaluated) return fail(EXQ_ERR_STATE, "exq_pei_batch: call exq_pei_eval first");
+    if (c->chosen_cap < batch_size) {
+        cudaFree(c->chosen);
+        c->chosen = nullptr;
+        c->chosen_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->chosen, (size_t)batch_size * sizeof(ArgPair)));
+        c->chosen_cap = batch_size;
+    }
+    for (int s = 0; s < batch_size; s++) {
+        ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+        select_best_kernel<<<1, 64, 0, g.stream>>>(c->best, c->Xc, c->d, c->xnew, c->chosen, s);
+        prof_end(m);
+        LAUNCH_CHECK("select_best_kernel");
+        int rc = pei_argmax_launch(gp, c, c->xnew);
+        if (rc) return rc;
+    }
+    std::vector<ArgPair> h(batch_size);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), c->chosen, batch_size * sizeof(ArgPair), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    for (int s = 0; s < batch_size; s++) {
+        if (idx) idx[s] = h[s].i;
+        if (val) val[s] = h[s].v;
+    }
+    return EXQ_OK;
+}
+
+int exq_cand_download(exq_cand_t c, int which, double* out) {
+    REQUIRE_READY();
+    if (!c || !out || which < 0 || which > 2) return fail(EXQ_ERR_ARG, "exq_cand_download: bad argument");
+    const double* src = which == 0 ? c->mean : which == 1 ? c->var : c->pei;
+    CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)c->M * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return EXQ_OK;
+}
+
+void* exq_cand_best_devptr(exq_cand_t c) { return c ? (void*)c->best : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Common device helpers for the EXAUQ B200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EXQ_TILE 128      // all dense matrices are padded to a multiple of this
+#define EXQ_MAX_D 64      // max input dimension supported by the kernels
+
+// kernel ids (order mirrors exauq/core/emulators.py:122-126)
+#define EXQ_KERNEL_MATERN52 0
+#define EXQ_KERNEL_SQEXP 1
+#define EXQ_KERNEL_PRODMAT52 2
+
+namespace exq {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- Ampere-style 16-byte async copy (LDGSTS) ------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- TMA 1-D bulk copy (cp.async.bulk -> UBLKCP) with an mbarrier ------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    while (!mbar_try_wait(bar, phase)) {
+    }
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col) -> SASS DMMA.8x8x4 ----
+// lane = 4*g + t:  a = A[g][t],  b = B[t][g],  c0,c1 = C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- covariance functions (mogp-emulator Kernel.py; call site exauq/core/emulators.py:122-126)
+// r2 = sum_k exp(corr_raw_k) (x_k - x'_k)^2
+__device__ __forceinline__ double corr_from_r2(int kernel_id, double r2) {
+    if (kernel_id == EXQ_KERNEL_MATERN52) {
+        double a = sqrt(5.0 * r2);
+        return (1.0 + a + (5.0 / 3.0) * r2) * exp(-a);
+    }
+    return exp(-0.5 * r2);
+}
+// d corr / d r2
+__device__ __forceinline__ double dcorr_dr2(int kernel_id, double r2) {
+    if (kernel_id == EXQ_KERNEL_MATERN52) {
+        double a = sqrt(5.0 * r2);
+        return (-5.0 / 6.0) * (1.0 + a) * exp(-a);
+    }
+    return -0.5 * exp(-0.5 * r2);
+}
+// 1-D Matern-5/2 factor for the product kernel
+__device__ __forceinline__ double mat52_1d(double r2) {
+    double a = sqrt(5.0 * r2);
+    return (1.0 + a + (5.0 / 3.0) * r2) * exp(-a);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace exq

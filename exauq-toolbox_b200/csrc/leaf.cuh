@@ -1,0 +1,216 @@
+// Leaf of the recursive factorisation: ONE CTA turns a 128 x 128 SPD diagonal block into
+// its Cholesky factor L (lower) and the inverse factor Linv = L^-1, entirely in shared
+// memory, with the O(n^3) parts on DMMA.8x8x4.
+//
+// Replaces (for one diagonal block) what the reference reaches through mogp's
+// jit_cholesky -> scipy.linalg.lapack.dpotrf (mogp GaussianProcess.fit via
+// exauq/core/emulators.py:447-448); failure (non-positive pivot) is reported through
+// `info` so that the host can apply mogp's adaptive-jitter retry policy.
+//
+// Layout: S[128][132] holds L in the lower triangle; the strictly-upper part is reused to
+// hold Linv TRANSPOSED (Linv[r][c], r > c, lives at S[c][r]); the sixteen 8 x 8 diagonal
+// blocks of Linv live in XD.  The 136 lower 8 x 8 tiles are owned round-robin by the 8
+// warps and stay in DMMA accumulator registers between steps (left-looking at tile level).
+#pragma once
+#include "exq_common.cuh"
+
+namespace exq {
+
+constexpr int LEAF_N = 128, LEAF_LD = 132, LEAF_NBLK = 16, LEAF_THREADS = 256;
+constexpr int LEAF_SLOTS = 17;        // 136 tiles / 8 warps
+constexpr int LEAF_XD_LD = 12;
+constexpr int LEAF_SMEM_DOUBLES =
+    LEAF_N * LEAF_LD + LEAF_NBLK * 8 * LEAF_XD_LD + LEAF_N + 8 * 8 * LEAF_XD_LD;
+constexpr int LEAF_SMEM_BYTES = LEAF_SMEM_DOUBLES * (int)sizeof(double);
+
+// A, Linv: pointers to the (row-major, leading dimension ld) full matrices of batch 0;
+// the leaf works on rows/cols [r0, r0+128).  info[batch] receives first bad column + 1.
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall, int64_t ld,
+                        int64_t strideA, int64_t strideL, int r0, int* __restrict__ info) {
+    extern __shared__ __align__(16) double leaf_smem[];
+    double* S = leaf_smem;
+    double* XD = S + LEAF_N * LEAF_LD;                 // [16][8][12]
+    double* rinv = XD + LEAF_NBLK * 8 * LEAF_XD_LD;    // [128]
+    double* scratch = rinv + LEAF_N;                   // [8 warps][8][12]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    double* A = Aall + (int64_t)blockIdx.x * strideA + (int64_t)r0 * ld + r0;
+    double* Li = Linvall + (int64_t)blockIdx.x * strideL + (int64_t)r0 * ld + r0;
+
+    // ---- tile ownership -------------------------------------------------------------
+    int tb[LEAF_SLOTS];       // (bi << 8) | bj, or -1
+    double c[LEAF_SLOTS][2];
+#pragma unroll
+    for (int s = 0; s < LEAF_SLOTS; s++) {
+        int q = warp + 8 * s;
+        int bj = 0, rem = q;
+        while (rem >= LEAF_NBLK - bj) { rem -= LEAF_NBLK - bj; bj++; }
+        int bi = bj + rem;
+        tb[s] = (q < 136) ? ((bi << 8) | bj) : -1;
+        c[s][0] = c[s][1] = 0.0;
+        if (tb[s] >= 0) {
+            int row = 8 * bi + g, col = 8 * bj + 2 * t;
+            double2 v = *reinterpret_cast<const double2*>(A + (int64_t)row * ld + col);
+            c[s][0] = (col <= row) ? v.x : 0.0;
+            c[s][1] = (col + 1 <= row) ? v.y : 0.0;
+            if (bj == 0) {
+                S[row * LEAF_LD + col] = c[s][0];
+                S[row * LEAF_LD + col + 1] = c[s][1];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ================= phase 1: Cholesky =================================================
+    for (int p = 0; p < LEAF_NBLK; p++) {
+        const int j0 = 8 * p;
+        // (a) 8 x 8 diagonal block, warp 0 (lanes >= 8 shadow lanes 0..7)
+        if (warp == 0) {
+            const int r = lane & 7;
+            double a[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) a[cc] = S[(j0 + r) * LEAF_LD + j0 + cc];
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++) {
+                double d = __shfl_sync(0xffffffffu, a[cc], cc);
+                double ri = rsqrt(d);
+                double l = d * ri;
+                if (r == cc) a[cc] = l;
+                else if (r > cc) a[cc] *= ri;
+#pragma unroll
+                for (int c2 = cc + 1; c2 < 8; c2++) {
+                    double lc = __shfl_sync(0xffffffffu, a[cc], c2);
+                    if (r >= c2) a[c2] -= a[cc] * lc;
+                }
+                if (lane == 0) {
+                    rinv[j0 + cc] = ri;
+                    if (!(d > 0.0) || !(d < 1.0e300)) atomicCAS(info + blockIdx.x, 0, r0 + j0 + cc + 1);
+                }
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++)
+                    if (cc <= r) S[(j0 + r) * LEAF_LD + j0 + cc] = a[cc];
+            }
+        }
+        __syncthreads();
+        // (b) rows below the diagonal block: forward substitution with L11; warp 7 inverts L11
+        {
+            const int r = j0 + 8 + tid;
+            if (r < LEAF_N) {
+                double a[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) a[cc] = S[r * LEAF_LD + j0 + cc];
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) {
+                    double s = a[cc];
+#pragma unroll
+                    for (int k = 0; k < cc; k++) s -= a[k] * S[(j0 + cc) * LEAF_LD + j0 + k];
+                    a[cc] = s * rinv[j0 + cc];
+                }
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++) S[r * LEAF_LD + j0 + cc] = a[cc];
+            }
+            if (warp == 7 && lane < 8) {
+                // column `lane` of inv(L11)
+                const int cc = lane;
+                double x[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < rr; k++)
+                        if (k >= cc) s += S[(j0 + rr) * LEAF_LD + j0 + k] * x[k];
+                    x[rr] = (rr < cc) ? 0.0 : ((rr == cc) ? rinv[j0 + rr] : -s * rinv[j0 + rr]);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) XD[(p * 8 + rr) * LEAF_XD_LD + cc] = x[rr];
+            }
+        }
+        __syncthreads();
+        // (c) rank-8 update of every trailing tile, in registers
+#pragma unroll
+        for (int s = 0; s < LEAF_SLOTS; s++) {
+            if (tb[s] < 0) continue;
+            const int bi = tb[s] >> 8, bj = tb[s] & 255;
+            if (bj <= p) continue;
+            double a0 = S[(8 * bi + g) * LEAF_LD + j0 + t];
+            double a1 = S[(8 * bi + g) * LEAF_LD + j0 + 4 + t];
+            double b0 = S[(8 * bj + g) * LEAF_LD + j0 + t];
+            double b1 = S[(8 * bj + g) * LEAF_LD + j0 + 4 + t];
+            dmma884(c[s][0], c[s][1], -a0, b0);
+            dmma884(c[s][0], c[s][1], -a1, b1);
+            if (bj == p + 1) {
+                int row = 8 * bi + g, col = 8 * bj + 2 * t;
+                S[row * LEAF_LD + col] = c[s][0];
+                S[row * LEAF_LD + col + 1] = c[s][1];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ================= phase 2: Linv = L^-1 ==============================================
+    // Y_ij = sum_{k=j}^{i-1} L_ik X_kj accumulates in registers; X_ij = -X_ii Y_ij.
+#pragma unroll
+    for (int s = 0; s < LEAF_SLOTS; s++) c[s][0] = c[s][1] = 0.0;
+    double* my_scratch = scratch + warp * 8 * LEAF_XD_LD;
+    for (int k = 0; k < LEAF_NBLK; k++) {
+        // (1) finalise block row k
+#pragma unroll
+        for (int s = 0; s < LEAF_SLOTS; s++) {
+            if (tb[s] < 0) continue;
+            const int bi = tb[s] >> 8, bj = tb[s] & 255;
+            if (bi != k || bj >= k) continue;
+            my_scratch[g * LEAF_XD_LD + 2 * t] = c[s][0];
+            my_scratch[g * LEAF_XD_LD + 2 * t + 1] = c[s][1];
+            __syncwarp();
+            double b0 = my_scratch[t * LEAF_XD_LD + g];
+            double b1 = my_scratch[(4 + t) * LEAF_XD_LD + g];
+            double a0 = XD[(k * 8 + g) * LEAF_XD_LD + t];
+            double a1 = XD[(k * 8 + g) * LEAF_XD_LD + 4 + t];
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, -a0, b0);
+            dmma884(d0, d1, -a1, b1);
+            // X[8k+g][8bj+2t(+1)] stored transposed
+            S[(8 * bj + 2 * t) * LEAF_LD + 8 * k + g] = d0;
+            S[(8 * bj + 2 * t + 1) * LEAF_LD + 8 * k + g] = d1;
+            __syncwarp();
+        }
+        __syncthreads();
+        // (2) Y_ij += L_ik X_kj for i > k >= j
+#pragma unroll
+        for (int s = 0; s < LEAF_SLOTS; s++) {
+            if (tb[s] < 0) continue;
+            const int bi = tb[s] >> 8, bj = tb[s] & 255;
+            if (bi <= k || bj > k) continue;
+            double a0 = S[(8 * bi + g) * LEAF_LD + 8 * k + t];
+            double a1 = S[(8 * bi + g) * LEAF_LD + 8 * k + 4 + t];
+            double b0, b1;
+            if (bj == k) {
+                b0 = XD[(k * 8 + t) * LEAF_XD_LD + g];
+                b1 = XD[(k * 8 + 4 + t) * LEAF_XD_LD + g];
+            } else {
+                b0 = S[(8 * bj + g) * LEAF_LD + 8 * k + t];
+                b1 = S[(8 * bj + g) * LEAF_LD + 8 * k + 4 + t];
+            }
+            dmma884(c[s][0], c[s][1], a0, b0);
+            dmma884(c[s][0], c[s][1], a1, b1);
+        }
+    }
+    __syncthreads();
+
+    // ---- write back L (upper zeroed) and Linv (full tile, zeros above the diagonal) ----
+    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
+        int r = idx >> 7, cc = idx & 127;
+        A[(int64_t)r * ld + cc] = (cc <= r) ? S[r * LEAF_LD + cc] : 0.0;
+        int br = r >> 3, bc = cc >> 3;
+        double v = 0.0;
+        if (bc < br) v = S[cc * LEAF_LD + r];
+        else if (bc == br) v = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7)];
+        Li[(int64_t)r * ld + cc] = v;
+    }
+}
+
+}  // namespace exq

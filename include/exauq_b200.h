@@ -1,0 +1,152 @@
+/*
+ * exauq_b200.h -- C ABI of libexauq_b200.so, the B200 (sm_100a) Gaussian-process engine that
+ * replaces the mogp-emulator/numpy arithmetic beneath EXAUQ-Toolbox's
+ * AbstractGaussianProcess interface (exauq/core/modelling.py:904-1138).
+ *
+ * The reference has no FFI: its "plugin API" is the Python ABC, implemented by
+ * MogpEmulator (exauq/core/emulators.py:69-667), which calls mogp-emulator.  Each entry
+ * point below names the reference call it replaces.  The Python host class
+ * (exauq-toolbox_b200/gp.py: B200GaussianProcess) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, float64 throughout, row-major host arrays.
+ *   - Return value: 0 = ok; < 0 = invalid argument / CUDA error (see exq_last_error());
+ *     > 0 = numerical condition (EXQ_NOT_PD: covariance not positive definite).
+ *   - Host pointers are owned by the caller; device memory is owned by the library behind
+ *     opaque handles.  One device per process (exq_init), one internal stream; calls are
+ *     synchronous with respect to the host unless stated.  Not thread-safe per handle.
+ *   - There is no CPU fallback: every compute entry point fails with EXQ_ERR_CUDA when no
+ *     B200 is present.
+ */
+#ifndef EXAUQ_B200_H
+#define EXAUQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXQ_OK 0
+#define EXQ_ERR_ARG (-1)
+#define EXQ_ERR_CUDA (-2)
+#define EXQ_ERR_STATE (-3) /* e.g. predict before fit */
+#define EXQ_NOT_PD 1       /* Cholesky met a non-positive pivot (mogp: LinAlgError) */
+
+/* kernel ids: table at exauq/core/emulators.py:122-126 */
+#define EXQ_MATERN52 0
+#define EXQ_SQEXP 1
+#define EXQ_PRODMAT52 2
+
+/* nugget modes: mogp GaussianProcess(nugget=...) as passed through exauq/core/emulators.py:129-141 */
+#define EXQ_NUGGET_FIXED 0    /* value supplied (float nugget, or 'fit' after estimation) */
+#define EXQ_NUGGET_ADAPTIVE 1 /* 0 unless Cholesky fails, then mean(diag K)*1e-6*10^k, k < 5 */
+
+typedef struct exq_gp_s* exq_gp_t;
+typedef struct exq_cand_s* exq_cand_t;
+
+/* ---- process / device ------------------------------------------------------------- */
+int exq_init(int device);              /* select device, create stream; idempotent per device */
+int exq_shutdown(void);
+const char* exq_last_error(void);
+int exq_device_sm_count(void);
+/* number of kernels this library launched since process start (bench.py "gpu_launches") */
+int64_t exq_launch_count(void);
+
+/* CUDA-event timing on the library stream (bench.py / roofline).  exq_timer_* brackets a
+ * region; exq_prof_* accumulates per-class kernel time between reset and get. */
+int exq_timer_start(void);
+int exq_timer_stop(double* ms);
+#define EXQ_PROF_GEMM_PREDICT 0 /* variance GEMM  Z = Linv Kc^T + column sum of squares */
+#define EXQ_PROF_GEMM_FACTOR 1  /* TRSM/SYRK/TRTRI/LAUUM tile GEMMs */
+#define EXQ_PROF_LEAF 2         /* 128 x 128 potrf+trtri leaves */
+#define EXQ_PROF_ASSEMBLE 3     /* covariance assembly */
+#define EXQ_PROF_STREAM 4       /* per-candidate epilogue, PEI update/argmax, vector kernels */
+#define EXQ_PROF_NCLASS 5
+int exq_prof_enable(int class_mask); /* bit i set: time launches of class i with event pairs */
+int exq_prof_reset(void);
+int exq_prof_get(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes);
+
+/* ---- correlation (stateless) ---------------------------------------------------------
+ * out[i*n2 + j] = kernel(A[i], B[j]; corr_raw).
+ * Replaces mogp Kernel.<name>().kernel_f(x1, x2, corr_raw) as called by
+ * MogpEmulator.correlation, exauq/core/emulators.py:495-567 (line 547). */
+int exq_corr(int kernel_id, int d, const double* corr_raw, const double* A, int64_t n1,
+             const double* B, int64_t n2, double* out);
+
+/* ---- a Gaussian process bound to training data -------------------------------------
+ * Replaces mogp GaussianProcess(inputs, targets, kernel=..., nugget=...) as constructed at
+ * exauq/core/emulators.py:414,447.  X is [N][d], y is [N]. */
+int exq_gp_create(int64_t N, int d, const double* X, const double* y, int kernel_id,
+                  exq_gp_t* out);
+int exq_gp_destroy(exq_gp_t gp);
+
+/* Fit with given hyperparameters: K = cov*C (+ nugget I), L = chol(K), Linv, alpha = K^-1 y.
+ * Replaces mogp GaussianProcess.fit(theta) as called by
+ * MogpEmulator._fit_gp_with_hyperparameters, exauq/core/emulators.py:418-450.
+ * corr_raw[d] = -2 ln(length scale), cov = process variance (linear scale).
+ * Outputs: nugget_used (the jitter in adaptive mode), logdet = log|K|, quad = y^T K^-1 y;
+ * the negative log-likelihood is 0.5*(logdet + quad + N ln 2 pi). */
+int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, int nugget_mode,
+               double* nugget_used, double* logdet, double* quad);
+
+/* Predictive mean and variance at M points Xc[M][d] (host):
+ * mean = k^T alpha, var = max(cov + nugget - k^T K^-1 k, 0).
+ * Replaces mogp GaussianProcess.predict as called by MogpEmulator.predict,
+ * exauq/core/emulators.py:612-667 (line 649), for a whole batch of inputs. */
+int exq_gp_predict(exq_gp_t gp, const double* Xc, int64_t M, double* mean, double* var);
+
+/* Leave-one-out sweep with the fitted hyperparameters: for every i, the prediction at x_i
+ * of the GP refitted on data \ {i}, and its NES error against y_i.
+ * Replaces the loop compute_loo_errors_gp runs, exauq/core/designers.py:263-272
+ * (compute_loo_gp :295-370, predict, nes_error exauq/core/modelling.py:754-825).
+ * Uses the closed form mu_i = y_i - [K^-1 y]_i / [K^-1]_ii, var_i = 1/[K^-1]_ii. */
+int exq_gp_loo(exq_gp_t gp, double* mean, double* var, double* nes);
+
+/* The same quantities by EXPLICIT refits (the reference's algorithm): for each of the cnt
+ * indices idx[], assemble the (N-1)-point system, factor it and predict at the left-out
+ * point.  Batched over the indices.  Used to validate exq_gp_loo and as a benchmark. */
+int exq_gp_loo_refit(exq_gp_t gp, const int* idx, int cnt, double* mean, double* var, double* nes);
+
+/* Inverse of the nugget-free covariance cov*C(train, train), out[N][N].
+ * Replaces AbstractGaussianProcess._compute_kinv, exauq/core/modelling.py:1095-1113
+ * (np.linalg.inv).  Returns EXQ_NOT_PD if that matrix is numerically singular. */
+int exq_gp_kinv(exq_gp_t gp, double* out);
+
+/* Negative log-likelihood and its gradient for R hyperparameter vectors at once.
+ * theta_raw[R][d+1] = (corr_raw[d], ln cov); nugget handling as in exq_gp_fit (one setting
+ * for all R).  val[r] = 0.5*(log|K| + y^T K^-1 y + N ln 2 pi); grad[r][d+1] = d val / d raw;
+ * info[r] = 0 or EXQ_NOT_PD; nugget_used[r] as in exq_gp_fit.  Priors are added by the host.
+ * Replaces mogp GaussianProcess.logposterior / logpost_deriv as driven by
+ * _fit_single_GP_MAP, exauq/utilities/mogp_fitting.py:289-346 (lines 318-324). */
+int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nugget,
+                         int nugget_mode, double* val, double* grad, int* info,
+                         double* nugget_used);
+
+/* ---- candidate sets resident in HBM (PEI maximisation over fixed candidates) -------- */
+int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out);
+int exq_cand_destroy(exq_cand_t c);
+
+/* Evaluate mean, variance and pseudo-expected improvement of the fitted GP at every
+ * candidate.  rep[n_rep][d] are the repulsion points other than the training inputs
+ * (pseudopoints, additional points); tmax is the largest training output.
+ * Replaces PEICalculator.compute = expected_improvement * repulsion,
+ * exauq/core/designers.py:522-553, 610-658, 660-706, evaluated per candidate. */
+int exq_pei_eval(exq_gp_t gp, exq_cand_t c, const double* rep, int n_rep, double tmax);
+/* arg max of the current PEI values (lowest index wins ties; NaN ignored) */
+int exq_pei_argmax(exq_cand_t c, int64_t* idx, double* val);
+/* A new design point x[d] joins the repulsion set: pei *= 1 - corr(., x)
+ * (PEICalculator.add_repulsion_points, exauq/core/designers.py:555-608, used at :835). */
+int exq_pei_add_point(exq_gp_t gp, exq_cand_t c, const double* x);
+/* batch_size rounds of (argmax, add chosen candidate) without host round trips;
+ * replaces the loop at exauq/core/designers.py:830-835 with a fixed candidate set. */
+int exq_pei_batch(exq_gp_t gp, exq_cand_t c, int batch_size, int64_t* idx, double* val);
+/* copy results back: which = 0 mean, 1 variance, 2 pei */
+int exq_cand_download(exq_cand_t c, int which, double* out);
+/* device address of the {double val; int64 idx} argmax pair, for NCCL allgather */
+void* exq_cand_best_devptr(exq_cand_t c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
