@@ -1,0 +1,623 @@
+"""``B200GaussianProcess``: drop-in ``AbstractGaussianProcess`` backed by libexauq_b200.so.
+
+Mirrors ``exauq.core.emulators.MogpEmulator`` (exauq/core/emulators.py:69-667) -- same
+constructor keywords, properties, argument checks and error types -- so that the
+reference's own ``exauq/core/designers.py`` (``compute_loo_gp``, ``compute_loo_errors_gp``,
+``PEICalculator``, ``compute_single_level_loo_samples``, ``compute_multi_level_loo_samples``)
+and ``MultiLevelGaussianProcess`` use it unchanged.  All arithmetic runs on the GPU through
+the C ABI (``_lib``); there is no CPU path.
+
+What differs from the reference, on purpose:
+
+* ``kinv`` is computed lazily on first access (the reference recomputes an SVD condition
+  number and ``np.linalg.inv`` inside every ``fit``, exauq/core/modelling.py:1082-1113);
+  a singular covariance therefore raises ``ValueError`` at first ``kinv`` access.
+* Fits with supplied hyperparameters on "parent data minus one point" -- what
+  ``compute_loo_gp`` does N times (exauq/core/designers.py:263-272, 365-369) -- are served
+  from ONE leave-one-out sweep of the parent on the GPU (``exq_gp_loo``); anything other
+  than predicting at the left-out input triggers a real refit.
+* Batched entry points the reference does not have: ``predict_batch``, ``loo_predictions``,
+  ``pei_candidates``, ``logpost_batch``.
+"""
+
+from __future__ import annotations
+
+import copy
+import itertools
+import math
+import threading
+from collections.abc import Collection, Sequence
+from numbers import Real
+from typing import Any, Optional
+from warnings import warn
+
+import numpy as np
+from scipy.linalg import LinAlgError
+from scipy.optimize import minimize
+
+from . import _lib
+from ._lib import DeviceCandidates, DeviceGP
+from .priors import MapPriors
+from .refapi import (
+    AbstractGaussianProcess,
+    GaussianProcessHyperparameters,
+    GaussianProcessPrediction,
+    Input,
+    TrainingDatum,
+)
+
+SUPPORTED_KERNELS = ("Matern52", "SquaredExponential", "ProductMat52")
+TOL = 1e-9  # exauq.core.numerics.FLOAT_TOLERANCE
+
+
+def inputs_to_array(inputs: Sequence[Input], dim: Optional[int] = None) -> np.ndarray:
+    """(n, d) float64 array of the coordinates of a sequence of ``Input``."""
+    rows = [np.atleast_1d(np.asarray(x.value, dtype=float)) if len(x) else np.empty(0) for x in inputs]
+    if dim is not None:
+        for r in rows:
+            if r.shape[0] != dim:
+                raise ValueError(
+                    f"Expected inputs to have dimension equal to {dim}, but "
+                    f"received input of dimension {r.shape[0]}."
+                )
+    return np.array(rows, dtype=float).reshape(len(rows), -1)
+
+
+def find_duplicate_rows(X: np.ndarray) -> Optional[tuple[int, int]]:
+    """First pair of rows equal within tolerance (rel 1e-9 or abs 1e-9 per coordinate, the rule
+    of exauq/core/numerics.py:31-73), found by a sort on the first coordinate instead of the
+    reference's O(N^2) Python loop (exauq/core/emulators.py:316-327)."""
+    n = X.shape[0]
+    if n < 2:
+        return None
+    order = np.argsort(X[:, 0], kind="stable")
+    x0 = X[order, 0]
+    slack = TOL * np.maximum(1.0, np.abs(x0)) * (1.0 + 1e-6)
+    hi = np.searchsorted(x0, x0 + 2.0 * slack, side="right")
+    for i in range(n):
+        j1 = hi[i]
+        if j1 <= i + 1:
+            continue
+        a = X[order[i]]
+        b = X[order[i + 1 : j1]]
+        close = np.abs(b - a) <= np.maximum(TOL * np.maximum(np.abs(a), np.abs(b)), TOL)
+        hit = np.nonzero(np.all(close, axis=1))[0]
+        if hit.size:
+            p, q = int(order[i]), int(order[i + 1 + hit[0]])
+            return (min(p, q), max(p, q))
+    return None
+
+
+class _FitState:
+    """Immutable result of one fit: training data, hyperparameters and the device handle.
+    Shared (not copied) between deep copies of a ``B200GaussianProcess``."""
+
+    def __init__(self, training_data, X, y, kernel, hyperparameters, corr_raw, dev: DeviceGP):
+        self.training_data = training_data
+        self.X, self.y = X, y
+        self.N, self.d = X.shape
+        self.kernel = kernel
+        self.hp = hyperparameters
+        self.corr_raw = corr_raw
+        self.dev = dev
+        self.ids = np.fromiter(map(id, training_data), dtype=np.int64, count=len(training_data))
+        self._loo = None
+        self._kinv = None
+        self._lock = threading.Lock()
+
+    def loo(self):
+        """(mean, var, nes) of the leave-one-out sweep; one GPU call, cached."""
+        with self._lock:
+            if self._loo is None:
+                self._loo = self.dev.loo()
+            return self._loo
+
+    def kinv(self) -> np.ndarray:
+        with self._lock:
+            if self._kinv is None:
+                try:
+                    self._kinv = self.dev.kinv()
+                except LinAlgError:
+                    raise ValueError(
+                        "Cannot compute covariance inverse: Covariance Matrix is, or too close to singular."
+                    ) from None
+            return self._kinv
+
+
+class _LooView:
+    """State of a GP 'fitted' to a parent's data minus one point with the parent's
+    hyperparameters, served from the parent's LOO sweep until something else is asked."""
+
+    def __init__(self, parent: _FitState, idx: int, training_data):
+        self.parent, self.idx, self.training_data = parent, idx, training_data
+        self.real: Optional[_FitState] = None
+
+
+class B200GaussianProcess(AbstractGaussianProcess):
+    """Gaussian process emulator computed on an NVIDIA B200.
+
+    Parameters
+    ----------
+    kernel : {"SquaredExponential", "Matern52", "ProductMat52"}
+        Covariance function (default "SquaredExponential", as ``MogpEmulator``).
+    nugget : {"adaptive", "fit", "pivot"} or float
+        Nugget handling (default "adaptive": 0 unless the Cholesky factorisation fails).
+        "pivot" is not available on this backend.
+    n_tries : int
+        Number of L-BFGS-B restarts in hyperparameter estimation (mogp default 15).
+    **kwargs :
+        ``inputs`` / ``targets`` are ignored as in ``MogpEmulator``; ``mean=None``,
+        ``priors=None``, ``inputdict``, ``use_patsy`` are accepted; anything else raises
+        ``RuntimeError`` (exauq/core/emulators.py:175-190).
+    """
+
+    def __init__(self, **kwargs):
+        kwargs = {k: v for k, v in kwargs.items() if k not in ("inputs", "targets")}
+        kernel = kwargs.pop("kernel", "SquaredExponential")
+        if kernel not in SUPPORTED_KERNELS:
+            raise ValueError(
+                f"Could not initialise {self.__class__.__name__} with kernel = {kernel}: not a "
+                "supported kernel function."
+            )
+        nugget = kwargs.pop("nugget", "adaptive")
+        self._n_tries = int(kwargs.pop("n_tries", 15))
+        mean = kwargs.pop("mean", None)
+        priors = kwargs.pop("priors", None)
+        kwargs.pop("inputdict", None)
+        kwargs.pop("use_patsy", None)
+        bad_nugget = (isinstance(nugget, str) and nugget not in ("adaptive", "fit", "pivot")) or (
+            not isinstance(nugget, str) and (not isinstance(nugget, Real) or nugget < 0)
+        )
+        if kwargs or mean is not None or priors is not None or bad_nugget or nugget == "pivot":
+            raise RuntimeError(
+                f"Could not construct the device Gaussian process during initialisation of "
+                f"{self.__class__.__name__}"
+            )
+        self._kernel_name = kernel
+        self._nugget = nugget
+        self._state: Optional[_FitState | _LooView] = None
+        self._loo_base: Optional[_FitState] = None
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def kernel(self) -> str:
+        return self._kernel_name
+
+    @property
+    def training_data(self) -> tuple[TrainingDatum]:
+        return self._state.training_data if self._state is not None else tuple()
+
+    @property
+    def fit_hyperparameters(self) -> Optional[GaussianProcessHyperparameters]:
+        if self._state is None:
+            return None
+        return self._state.parent.hp if isinstance(self._state, _LooView) else self._state.hp
+
+    @property
+    def kinv(self) -> np.ndarray:
+        if self._state is None:
+            return np.array([])
+        return self._real_state().kinv()
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_state", "_loo_base"):
+                setattr(new, k, v)  # immutable fit results (incl. device buffers) are shared
+            else:
+                setattr(new, k, copy.deepcopy(v, memo))
+        return new
+
+    # ------------------------------------------------------------------ fitting
+    def fit(
+        self,
+        training_data: Collection[TrainingDatum],
+        hyperparameters: Optional[GaussianProcessHyperparameters] = None,
+        hyperparameter_bounds: Optional[Sequence] = None,
+    ) -> None:
+        """Fit to data; signature, checks and errors as ``MogpEmulator.fit``
+        (exauq/core/emulators.py:220-313)."""
+        training_data = self._parse_training_data(training_data)
+        if not training_data:
+            return None
+
+        if not (hyperparameters is None or isinstance(hyperparameters, GaussianProcessHyperparameters)):
+            raise TypeError(
+                "Expected 'hyperparameters' to be None or of type "
+                f"{GaussianProcessHyperparameters.__name__}, but received {type(hyperparameters)} instead."
+            )
+
+        view = self._match_loo(training_data, hyperparameters)
+        if view is not None:
+            self._validate_hyperparameter_bounds(hyperparameter_bounds)
+            self._state = view
+            return None
+
+        X = inputs_to_array([datum.input for datum in training_data])
+        y = np.array([datum.output for datum in training_data], dtype=float)
+        dup = find_duplicate_rows(X)
+        if dup is not None:
+            a, b = training_data[dup[0]].input, training_data[dup[1]].input
+            raise ValueError(
+                f"Points {np.round(a, 9)} and {np.round(b, 9)}" " in 'TrainingDatum' are not unique within tolerance."
+            )
+        self._validate_hyperparameter_bounds(hyperparameter_bounds)
+
+        if hyperparameters is None:
+            state = self._fit_with_estimation(training_data, X, y, hyperparameter_bounds)
+        elif self._nugget == "fit" and hyperparameters.nugget is None:
+            raise ValueError(
+                "The underlying Gaussian process was created with 'nugget'='fit', "
+                "but the nugget supplied during fitting is "
+                f"{hyperparameters.nugget}, when it should instead be a float."
+            )
+        else:
+            state = self._fit_with_hyperparameters(training_data, X, y, hyperparameters)
+
+        n_params = X.shape[1] + 1 + (1 if self._nugget == "fit" else 0)
+        if len(training_data) < n_params:
+            warn(
+                f"Fewer training points ({len(training_data)}) than hyperparameters ({n_params}) being "
+                f"estimated. Estimates may be unreliable."
+            )
+        self._state = state
+        self._loo_base = state
+        return None
+
+    def _match_loo(self, data, hp) -> Optional[_LooView]:
+        """Recognise ``parent.training_data`` minus one element refitted with the parent's
+        hyperparameters (exauq/core/designers.py:365-369)."""
+        base = self._loo_base
+        if base is None or hp is None or len(data) != base.N - 1 or base.N < 2:
+            return None
+        if not (hp is base.hp or hp == base.hp):
+            return None
+        ids = np.fromiter(map(id, data), dtype=np.int64, count=len(data))
+        diff = np.nonzero(ids != base.ids[:-1])[0]
+        idx = int(diff[0]) if diff.size else base.N - 1
+        if not np.array_equal(ids[idx:], base.ids[idx + 1 :]):
+            return None
+        return _LooView(base, idx, data)
+
+    def _nugget_args(self, hp: GaussianProcessHyperparameters):
+        """(value, adaptive?) following exauq/core/emulators.py:427-445; a supplied numeric
+        nugget becomes this emulator's nugget setting from then on (the reference mutates
+        its kwargs in place at :433)."""
+        if hp.nugget is not None:
+            self._nugget = float(hp.nugget)
+            return float(hp.nugget), False
+        if isinstance(self._nugget, Real):
+            return float(self._nugget), False
+        return 0.0, True  # "adaptive"
+
+    def _fit_with_hyperparameters(self, training_data, X, y, hp) -> _FitState:
+        if len(hp.corr_length_scales) != X.shape[1]:
+            raise ValueError(
+                f"Expected {X.shape[1]} correlation length scales but received {len(hp.corr_length_scales)}."
+            )
+        corr_raw = np.array([GaussianProcessHyperparameters.transform_corr(c) for c in hp.corr_length_scales])
+        nugget, adaptive = self._nugget_args(hp)
+        dev = DeviceGP(X, y, self._kernel_name)
+        dev.fit(corr_raw, float(hp.process_var), nugget, adaptive)
+        fitted = GaussianProcessHyperparameters(
+            corr_length_scales=np.array(hp.corr_length_scales, dtype=float),
+            process_var=float(hp.process_var),
+            nugget=float(dev.nugget_used),
+        )
+        return _FitState(training_data, X, y, self._kernel_name, fitted, corr_raw, dev)
+
+    def _fit_with_estimation(self, training_data, X, y, bounds) -> _FitState:
+        """MAP estimation: multi-restart L-BFGS-B on the negative log-posterior, as
+        ``fit_GP_MAP`` / ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:51-346), with
+        objective and gradient evaluated on the GPU for all restarts at once."""
+        if self._nugget == "fit":
+            raise NotImplementedError("nugget='fit' estimation is not available on this backend yet")
+        raw_bounds = self._compute_raw_param_bounds(bounds) if bounds is not None else None
+        d = X.shape[1]
+        dev = DeviceGP(X, y, self._kernel_name)
+        priors = MapPriors(X)
+        nugget = 0.0 if isinstance(self._nugget, str) else float(self._nugget)
+        adaptive = isinstance(self._nugget, str)
+        starts = [priors.sample() for _ in range(self._n_tries)]
+        best = run_map_restarts(dev, priors, starts, raw_bounds, nugget, adaptive)
+        if best is None:
+            raise RuntimeError("GP fitting failed")
+        theta = best
+        dev.fit(theta[:d], float(np.exp(theta[d])), nugget, adaptive)
+        fitted = GaussianProcessHyperparameters(
+            corr_length_scales=np.exp(-0.5 * theta[:d]),
+            process_var=float(np.exp(theta[d])),
+            nugget=float(dev.nugget_used),
+        )
+        return _FitState(training_data, X, y, self._kernel_name, fitted, np.array(theta[:d]), dev)
+
+    # ---- argument validation, as the reference ---------------------------------------------
+    @staticmethod
+    def _parse_training_data(training_data: Any) -> tuple[TrainingDatum]:
+        if training_data is None:
+            return tuple()
+        try:
+            _ = len(training_data)
+            if not all(isinstance(x, TrainingDatum) for x in training_data):
+                raise TypeError
+            return tuple(training_data)
+        except TypeError:
+            raise TypeError(
+                f"Expected 'training_data' to be of type finite collection of TrainingDatum, "
+                f"but received {type(training_data)} instead."
+            )
+
+    def _validate_hyperparameter_bounds(self, hyperparameter_bounds) -> None:
+        if hyperparameter_bounds is None:
+            return None
+        for i, bound in enumerate(hyperparameter_bounds):
+            try:
+                self._validate_bound_pair(bound)
+            except (TypeError, ValueError) as e:
+                raise e.__class__(f"Invalid bound {bound} at index {i} of 'hyperparameter_bounds': {e}")
+        return None
+
+    @staticmethod
+    def _validate_bound_pair(bounds: Sequence):
+        try:
+            if not len(bounds) == 2:
+                raise ValueError(
+                    "Expected 'bounds' to be a sequence of length 2, but " f"got length {len(bounds)}."
+                )
+        except TypeError:
+            raise TypeError(f"Expected 'bounds' to be of type sequence, but received {type(bounds)} instead.")
+        if not all(bound is None or isinstance(bound, Real) for bound in bounds):
+            raise TypeError(
+                f"Expected each 'bound' in {bounds} to be None or of type {Real} "
+                "but one or more elements were of an unexpected type."
+            )
+        lower, upper = bounds
+        if lower is not None and upper is not None and upper < lower:
+            raise ValueError(
+                "Lower bound must be less than or equal to upper bound, but received "
+                f"lower bound = {lower} and upper bound = {upper}."
+            )
+
+    @staticmethod
+    def _compute_raw_param_bounds(bounds):
+        """Linear-scale bounds -> raw bounds (exauq/core/emulators.py:453-485): correlation
+        bounds swap because -2 ln is decreasing."""
+        for _, upper in bounds:
+            if upper is not None and upper <= 0:
+                raise ValueError("Upper bounds must be positive numbers")
+        tc = lambda v: GaussianProcessHyperparameters.transform_corr(v) if v is not None else None  # noqa: E731
+        tv = lambda v: GaussianProcessHyperparameters.transform_cov(v) if v is not None else None  # noqa: E731
+        raw = [(tc(b[1]), tc(b[0])) for b in bounds[:-1]] + [(tv(bounds[-1][0]), tv(bounds[-1][1]))]
+        return tuple(raw)
+
+    # ------------------------------------------------------------------ state helpers
+    def _real_state(self) -> _FitState:
+        """The fitted state, materialising a LOO view into a real (N-1)-point fit if needed."""
+        st = self._state
+        if isinstance(st, _LooView):
+            if st.real is None:
+                keep = np.arange(st.parent.N) != st.idx
+                st.real = self._fit_with_hyperparameters(
+                    st.training_data, st.parent.X[keep], st.parent.y[keep], st.parent.hp
+                )
+            return st.real
+        return st
+
+    def _input_dim(self) -> Optional[int]:
+        st = self._state
+        if st is None:
+            return None
+        return st.parent.d if isinstance(st, _LooView) else st.d
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, x: Input) -> GaussianProcessPrediction:
+        """As ``MogpEmulator.predict`` (exauq/core/emulators.py:612-667)."""
+        if not isinstance(x, Input):
+            raise TypeError(f"Expected 'x' to be of type Input, but received {type(x)} instead.")
+        if len(self.training_data) == 0:
+            raise RuntimeError("Cannot make prediction because emulator has not been trained on any data.")
+        if not len(x) == (expected_dim := self._input_dim()):
+            raise ValueError(
+                f"Expected 'x' to be an Input with {expected_dim} coordinates, but " f"it has {len(x)} instead."
+            )
+        st = self._state
+        if isinstance(st, _LooView) and st.real is None:
+            left_out = st.parent.training_data[st.idx].input
+            if x is left_out or x == left_out:
+                mean, var, _ = st.parent.loo()
+                return GaussianProcessPrediction(estimate=float(mean[st.idx]), variance=float(var[st.idx]))
+        mean, var = self._real_state().dev.predict(inputs_to_array([x]))
+        return GaussianProcessPrediction(estimate=float(mean[0]), variance=float(var[0]))
+
+    def predict_batch(self, X) -> tuple[np.ndarray, np.ndarray]:
+        """Predictive means and variances at the rows of ``X`` (or a sequence of ``Input``)."""
+        if len(self.training_data) == 0:
+            raise RuntimeError("Cannot make prediction because emulator has not been trained on any data.")
+        if len(X) and isinstance(X[0], Input):
+            X = inputs_to_array(X, self._input_dim())
+        X = np.asarray(X, dtype=float).reshape(-1, self._input_dim())
+        return self._real_state().dev.predict(X)
+
+    def loo_predictions(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Means, variances and NES errors of the N leave-one-out refits (fixed
+        hyperparameters), the quantities ``compute_loo_errors_gp`` collects
+        (exauq/core/designers.py:263-272)."""
+        if len(self.training_data) < 2:
+            raise ValueError("Cannot compute leave one out error: fewer than 2 training points.")
+        return self._real_state().loo()
+
+    # ------------------------------------------------------------------ correlation
+    def correlation(self, inputs1: Sequence[Input], inputs2: Sequence[Input]) -> np.ndarray:
+        """As ``MogpEmulator.correlation`` (exauq/core/emulators.py:495-567)."""
+        try:
+            if len(inputs1) == 0 or len(inputs2) == 0:
+                return np.array([])
+        except TypeError:
+            raise TypeError(
+                "Expected 'inputs1' and 'inputs2' to be of type sequences of Input objects, "
+                f"but received {type(inputs1)} and {type(inputs2)} instead."
+            )
+        if not (all(isinstance(x, Input) for x in inputs1) and all(isinstance(x, Input) for x in inputs2)):
+            raise TypeError(
+                "Expected all 'inputs1' and 'inputs2' to be of type Input objects, "
+                "but one or more elements were of an unexpected type."
+            )
+        assert self._state is not None, (
+            f"Cannot calculate correlations for this instance of {self.__class__} "
+            "because it hasn't yet been trained on data."
+        )
+        expected_dim = self._input_dim()
+        wrong = [len(x) for x in itertools.chain(inputs1, inputs2) if len(x) != expected_dim]
+        if wrong:
+            raise ValueError(
+                f"Expected inputs to have dimension equal to {expected_dim}, but "
+                f"received input of dimension {wrong[0]}."
+            )
+        st = self._state
+        corr_raw = st.parent.corr_raw if isinstance(st, _LooView) else st.corr_raw
+        return _lib.corr(self._kernel_name, corr_raw, inputs_to_array(inputs1), inputs_to_array(inputs2))
+
+    def covariance_matrix(self, inputs: Sequence[Input]) -> np.ndarray:
+        """As ``MogpEmulator.covariance_matrix`` (exauq/core/emulators.py:569-610)."""
+        try:
+            return super().covariance_matrix(inputs)
+        except TypeError:
+            if not isinstance(inputs, Sequence):
+                raise TypeError(
+                    "Expected 'inputs' to be of type sequence of Input objects, but received "
+                    f"{type(inputs)} instead."
+                ) from None
+            else:
+                raise TypeError(
+                    "Expected all elements of 'inputs' to be of type Input objects, "
+                    "but one or more elements were of an unexpected type."
+                ) from None
+
+    # ------------------------------------------------------------------ batched extras
+    def logpost_batch(self, theta_raw, with_prior: bool = True):
+        """Negative log-posterior (or likelihood) and gradient at R raw parameter vectors
+        ``(corr_raw..., ln cov)`` for the current training data, all on the GPU."""
+        st = self._real_state()
+        theta_raw = np.asarray(theta_raw, dtype=float).reshape(-1, st.d + 1)
+        nugget = 0.0 if isinstance(self._nugget, str) else float(self._nugget)
+        val, grad, info, _ = st.dev.logpost_batch(theta_raw, nugget, isinstance(self._nugget, str))
+        if with_prior:
+            pri = MapPriors(st.X)
+            for r in range(theta_raw.shape[0]):
+                val[r] -= pri.logp(theta_raw[r])
+                grad[r] -= pri.dlogp_draw(theta_raw[r])
+        return val, grad, info
+
+    def pei_candidates(self, candidates, repulsion_points, batch_size: int = 1, max_target: Optional[float] = None):
+        """Pseudo-expected improvement of this GP (as ``PEICalculator.compute``,
+        exauq/core/designers.py:522-706) over a fixed candidate array, and ``batch_size``
+        rounds of arg max + repulsion update (the loop at :830-835).  Returns the chosen
+        indices, their PEI values and the ``DeviceCandidates`` (for downloading arrays)."""
+        st = self._real_state()
+        cand = candidates if isinstance(candidates, DeviceCandidates) else DeviceCandidates(candidates)
+        tmax = float(np.max(st.y)) if max_target is None else float(max_target)
+        rep = np.asarray(repulsion_points, dtype=float).reshape(-1, st.d) if len(repulsion_points) else None
+        cand.pei_eval(st.dev, rep, tmax)
+        idx, val = cand.batch(st.dev, batch_size)
+        return idx, val, cand
+
+
+# =========================================================================================
+# MAP estimation driver
+# =========================================================================================
+class _Rendezvous:
+    """Batches objective evaluations requested concurrently by the restart threads into one
+    ``exq_gp_logpost_batch`` call per round (hard part 5)."""
+
+    def __init__(self, dev: DeviceGP, n_workers: int, nugget: float, adaptive: bool):
+        self.dev, self.nugget, self.adaptive = dev, nugget, adaptive
+        self.active = n_workers
+        self.cv = threading.Condition()
+        self.pending: dict[int, np.ndarray] = {}
+        self.results: dict[int, tuple] = {}
+        self.n_batches = 0
+        self.n_evals = 0
+
+    def _flush_locked(self):
+        keys = sorted(self.pending)
+        thetas = np.array([self.pending[k] for k in keys])
+        self.pending.clear()
+        try:
+            val, grad, info, _ = self.dev.logpost_batch(thetas, self.nugget, self.adaptive)
+            for i, k in enumerate(keys):
+                self.results[k] = (val[i], grad[i], int(info[i]), None)
+        except Exception as exc:  # propagate to every waiting worker
+            for k in keys:
+                self.results[k] = (None, None, -1, exc)
+        self.n_batches += 1
+        self.n_evals += len(keys)
+        self.cv.notify_all()
+
+    def evaluate(self, wid: int, theta: np.ndarray):
+        with self.cv:
+            self.pending[wid] = np.array(theta, dtype=float)
+            if len(self.pending) >= self.active:
+                self._flush_locked()
+            while wid not in self.results:
+                self.cv.wait()
+            return self.results.pop(wid)
+
+    def retire(self):
+        with self.cv:
+            self.active -= 1
+            if self.pending and len(self.pending) >= self.active:
+                self._flush_locked()
+
+
+def run_map_restarts(dev: DeviceGP, priors: MapPriors, starts, raw_bounds, nugget: float, adaptive: bool,
+                     stats: Optional[dict] = None) -> Optional[np.ndarray]:
+    """One scipy L-BFGS-B minimisation per starting point, as the restart loop of
+    ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:309-335); each optimiser runs in
+    its own thread and all objective/gradient requests of a round are evaluated in one
+    batched GPU call.  Restarts that hit a non-positive-definite covariance or a floating
+    point overflow are skipped (:332-335).  Returns the raw parameters with the lowest
+    negative log-posterior, or None if every restart failed."""
+    d = dev.d
+    rv = _Rendezvous(dev, len(starts), nugget, adaptive)
+    out: list[Optional[tuple[float, np.ndarray]]] = [None] * len(starts)
+
+    def worker(wid: int, theta0: np.ndarray):
+        cache: dict[bytes, tuple[float, np.ndarray]] = {}
+
+        def fg(theta):
+            key = np.asarray(theta, dtype=float).tobytes()
+            if key not in cache:
+                cache.clear()
+                if not np.all(np.isfinite(np.exp(theta[: d + 1]))):
+                    raise FloatingPointError("overflow in hyperparameter transform")
+                val, grad, info, exc = rv.evaluate(wid, theta)
+                if exc is not None:
+                    raise exc
+                if info != 0 or not np.isfinite(val):
+                    raise LinAlgError("covariance matrix is not positive definite")
+                cache[key] = (float(val - priors.logp(theta)), grad - priors.dlogp_draw(theta))
+            return cache[key]
+
+        try:
+            with np.errstate(divide="raise", over="raise", invalid="raise"):
+                res = minimize(lambda t: fg(t)[0], theta0, method="L-BFGS-B", jac=lambda t: fg(t)[1],
+                               bounds=raw_bounds)
+            out[wid] = (float(res["fun"]), np.array(res["x"], dtype=float))
+        except (LinAlgError, FloatingPointError):
+            out[wid] = None
+        finally:
+            rv.retire()
+
+    threads = [threading.Thread(target=worker, args=(i, s), daemon=True) for i, s in enumerate(starts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if stats is not None:
+        stats.update(batches=rv.n_batches, evals=rv.n_evals)
+    done = [o for o in out if o is not None]
+    if not done:
+        return None
+    vals = np.array([o[0] for o in done])
+    return done[int(np.argmin(vals))][1]

@@ -1,0 +1,100 @@
+"""Default hyperparameter priors used by MAP estimation (host side, O(d) work).
+
+The reference estimates hyperparameters by minimising mogp's negative log-POSTERIOR
+(exauq/utilities/mogp_fitting.py:289-346); with ``priors=None`` -- the only case
+``MogpEmulator`` reaches (exauq/core/emulators.py:129-137) -- mogp-emulator 0.7.2 puts, per
+input dimension, an inverse-gamma prior on the correlation length whose cdf is 0.005 at the
+median gap between sorted unique coordinates and 0.995 at their range, a flat prior on the
+process variance, and (only when the nugget is fitted) an inverse-gamma prior on the nugget
+with the same construction on (1e-8, 1e-6).  Densities act on the linear-scale parameter;
+no Jacobian term.  Starting points are drawn from these priors (flat ones from U(-2.5, 2.5)
+on the raw scale) through numpy's global RNG, in parameter order, so that seeding
+``np.random`` reproduces the reference's restarts.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import scipy.stats
+from scipy.optimize import root
+from scipy.special import gammaln
+
+
+def _solve_invgamma(lo: float, hi: float) -> Optional[tuple[float, float]]:
+    """(shape, scale) with cdf(lo) = 0.005 and cdf(hi) = 0.995, or None if the solver fails."""
+
+    def resid(z):
+        a, b = np.exp(z[0]), np.exp(z[1])
+        cdf = scipy.stats.invgamma.cdf
+        return np.array([cdf(lo, a, scale=b) - 0.005, cdf(hi, a, scale=b) - 0.995])
+
+    with np.errstate(all="ignore"):
+        sol = root(resid, np.zeros(2))
+    if not sol["success"]:
+        return None
+    return float(np.exp(sol["x"][0])), float(np.exp(sol["x"][1]))
+
+
+class MapPriors:
+    """Priors on (corr lengths..., process variance[, nugget]) for one training set."""
+
+    def __init__(self, X: np.ndarray, fit_nugget: bool = False):
+        X = np.asarray(X, dtype=float)
+        self.d = X.shape[1]
+        self.corr = []  # per dimension: (shape, scale) or None for a flat prior
+        for col in X.T:
+            u = np.unique(col)
+            gap = float(np.median(np.diff(u))) if u.size > 2 else 0.0
+            span = float(u[-1] - u[0]) if u.size > 1 else 0.0
+            self.corr.append(_solve_invgamma(gap, span) if gap > 0.0 and span > 0.0 else None)
+        self.nugget = _solve_invgamma(1.0e-8, 1.0e-6) if fit_nugget else None
+        self.fit_nugget = fit_nugget
+
+    # -- log density and its gradient w.r.t. the raw parameters ---------------------------
+    @staticmethod
+    def _logp(x: float, prm) -> float:
+        if prm is None:
+            return 0.0
+        a, b = prm
+        return float(a * np.log(b) - gammaln(a) - (a + 1.0) * np.log(x) - b / x)
+
+    @staticmethod
+    def _dlogp_dx(x: float, prm) -> float:
+        if prm is None:
+            return 0.0
+        a, b = prm
+        return float(-(a + 1.0) / x + b / x**2)
+
+    def logp(self, theta_raw: np.ndarray) -> float:
+        lengths = np.exp(-0.5 * theta_raw[: self.d])
+        total = sum(self._logp(x, prm) for x, prm in zip(lengths, self.corr))
+        if self.fit_nugget:
+            total += self._logp(float(np.exp(theta_raw[self.d + 1])), self.nugget)
+        return total
+
+    def dlogp_draw(self, theta_raw: np.ndarray) -> np.ndarray:
+        out = np.zeros_like(theta_raw, dtype=float)
+        lengths = np.exp(-0.5 * theta_raw[: self.d])
+        for k, (x, prm) in enumerate(zip(lengths, self.corr)):
+            out[k] = self._dlogp_dx(x, prm) * (-0.5 * x)      # d length / d raw = -length / 2
+        if self.fit_nugget:
+            nu = float(np.exp(theta_raw[self.d + 1]))
+            out[self.d + 1] = self._dlogp_dx(nu, self.nugget) * nu
+        return out
+
+    # -- starting points ------------------------------------------------------------------
+    @staticmethod
+    def _draw(prm, to_raw) -> float:
+        if prm is None:
+            return float(5.0 * (np.random.rand() - 0.5))
+        a, b = prm
+        return float(to_raw(scipy.stats.invgamma.rvs(a, scale=b)))
+
+    def sample(self) -> np.ndarray:
+        pt = [self._draw(prm, lambda x: -2.0 * np.log(x)) for prm in self.corr]
+        pt.append(self._draw(None, None))                     # process variance: flat
+        if self.fit_nugget:
+            pt.append(self._draw(self.nugget, np.log))
+        return np.array(pt, dtype=float)

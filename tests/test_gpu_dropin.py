@@ -1,0 +1,181 @@
+"""B200GaussianProcess used by the reference's UNCHANGED designers, compared with the
+reference's MogpEmulator (running on the oracle's mogp restatement) on the same inputs."""
+
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, needs_exauq
+
+pytestmark = [pytest.mark.gpu, needs_exauq]
+
+
+@pytest.fixture(scope="module")
+def api():
+    import exauq.core.designers as designers
+    from exauq.core.emulators import MogpEmulator, MogpHyperparameters
+    from exauq.core.modelling import (GaussianProcessHyperparameters, Input, MultiLevel,
+                                      MultiLevelGaussianProcess, SimulatorDomain, TrainingDatum)
+
+    from exauq_toolbox_b200.gp import B200GaussianProcess
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.__dict__.update(locals())
+    return ns
+
+
+def close(a, b, rel=1e-8, abs_=1e-9):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return bool(np.all(np.abs(a - b) <= np.maximum(rel * np.maximum(np.abs(a), np.abs(b)), abs_)))
+
+
+def _data(api, g):
+    return [api.TrainingDatum(api.Input(*x), y) for x, y in zip(g["X"] if "X" in g else g["inputs"],
+                                                               g["y"] if "y" in g else g["outputs"])]
+
+
+def test_fit_predict_correlation_match_reference(api):
+    g = load_golden("fixed_matern_d3_n40.json")
+    data = _data(api, g)
+    hp = g["hyperparameters"]
+    ref = api.MogpEmulator(kernel="Matern52")
+    ref.fit(data, hyperparameters=api.MogpHyperparameters(hp["corr_length_scales"], hp["process_var"], hp["nugget"]))
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    assert gp.training_data == () and gp.fit_hyperparameters is None and gp.kinv.size == 0
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters(hp["corr_length_scales"], hp["process_var"],
+                                                                   hp["nugget"]))
+    assert gp.training_data == tuple(data)
+    assert gp.fit_hyperparameters == api.GaussianProcessHyperparameters(hp["corr_length_scales"],
+                                                                        hp["process_var"], hp["nugget"])
+    qs = [api.Input(*q) for q in g["query"]]
+    for q in qs:
+        a, b = gp.predict(q), ref.predict(q)
+        assert close(a.estimate, b.estimate) and close(a.variance, b.variance)
+    train_inputs = [d.input for d in data]
+    assert np.max(np.abs(gp.correlation(qs, train_inputs) - ref.correlation(qs, train_inputs))) < 1e-13
+    assert np.allclose(gp.covariance_matrix(qs), ref.covariance_matrix(qs), rtol=1e-13)
+    assert np.allclose(gp.kinv, ref.kinv, rtol=1e-6, atol=1e-7 * np.max(np.abs(ref.kinv)))
+    assert gp.correlation([], train_inputs).size == 0
+    with pytest.raises(TypeError):
+        gp.predict([0.1, 0.2, 0.3])
+    with pytest.raises(ValueError):
+        gp.predict(api.Input(0.1, 0.2))
+    with pytest.raises(ValueError):
+        gp.fit(data + [data[0]])
+
+
+def test_unchanged_loo_designers_are_served_from_one_sweep(api):
+    """compute_loo_gp / compute_loo_prediction (exauq/core/designers.py:295-370, 958-998)
+    called exactly as the reference's compute_loo_errors_gp does."""
+    g = load_golden("fixed_matern_d8_n150.json")
+    data = _data(api, g)
+    hp = g["hyperparameters"]
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters(hp["corr_length_scales"], hp["process_var"],
+                                                                   hp["nugget"]))
+    from exauq_toolbox_b200 import _lib
+
+    loo_gp = copy.deepcopy(gp)
+    n0 = _lib.launch_count()
+    got = []
+    for i, datum in enumerate(gp.training_data):
+        api.designers.compute_loo_gp(gp, i, loo_gp=loo_gp)
+        assert len(loo_gp.training_data) == len(data) - 1
+        pr = loo_gp.predict(datum.input)
+        got.append([pr.estimate, pr.variance, pr.nes_error(datum.output)])
+    assert _lib.launch_count() - n0 < 20, "the N refits must be served by one LOO sweep"
+    got, ref = np.array(got), np.array(g["loo"])
+    assert close(got[:, 0], ref[:, 0]) and close(got[:, 1], ref[:, 1]) and close(got[:, 2], ref[:, 2])
+    # asking a LOO GP anything else triggers a real refit of the N-1 system
+    api.designers.compute_loo_gp(gp, 3, loo_gp=loo_gp)
+    q = api.Input(*g["query"][0])
+    refgp = api.MogpEmulator(kernel="Matern52")
+    refgp.fit(data[:3] + data[4:], hyperparameters=api.MogpHyperparameters(hp["corr_length_scales"],
+                                                                          hp["process_var"], hp["nugget"]))
+    a, b = loo_gp.predict(q), refgp.predict(q)
+    assert close(a.estimate, b.estimate) and close(a.variance, b.variance)
+    # and the user-visible state of a deep copy is independent
+    loo_gp.custom_attribute = [1, 2]
+    c = copy.deepcopy(loo_gp)
+    c.custom_attribute.append(3)
+    assert loo_gp.custom_attribute == [1, 2]
+
+
+def test_config1_single_level_loo_samples(api):
+    """BASELINE.json configs[0]: N=50 LHS on the 2-D toy simulator, Matern-5/2, then
+    compute_single_level_loo_samples(batch_size=1) through the unchanged designers; golden
+    values were produced by the reference's MogpEmulator with the same numpy seeds."""
+    g = load_golden("slas_config1.json")
+    domain = api.SimulatorDomain([tuple(b) for b in g["domain"]])
+    data = _data(api, g)
+    np.random.seed(g["gp_fit_seed"])
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data)
+    hp, ref = gp.fit_hyperparameters, g["gp_hyperparameters"]
+    # the reference's own tests compare estimated hyperparameters at 1e-5 (test_emulators.py:497-516)
+    assert np.allclose(hp.corr_length_scales, ref["corr_length_scales"], rtol=1e-5)
+    assert np.isclose(hp.process_var, ref["process_var"], rtol=1e-5)
+    assert hp.nugget == ref["nugget"]
+    np.random.seed(g["errors_gp_fit_seed"])
+    gp_e = api.designers.compute_loo_errors_gp(gp, domain)
+    nes = np.array([d.output for d in gp_e.training_data])
+    assert np.allclose(nes, g["loo_nes_errors"], rtol=1e-4)
+    hpe, refe = gp_e.fit_hyperparameters, g["errors_gp_hyperparameters"]
+    assert np.allclose(hpe.corr_length_scales, refe["corr_length_scales"], rtol=1e-4)
+    assert np.isclose(hpe.process_var, refe["process_var"], rtol=1e-4)
+    np.random.seed(g["errors_gp_fit_seed"])
+    new = api.designers.compute_single_level_loo_samples(gp, domain, batch_size=1, seed=g["de_seed"])
+    assert np.allclose(np.array(new[0]), g["new_design_point"], atol=2e-3)
+
+
+def test_multi_level_gp_and_loo(api):
+    """MultiLevelGaussianProcess (exauq/core/modelling.py:1352-1706) and the multi-level LOO
+    prediction (exauq/core/designers.py:840-922) with B200 GPs vs reference GPs."""
+    rng = np.random.default_rng(4)
+    d = 2
+    X1, X2 = rng.uniform(0, 1, (24, d)), rng.uniform(0, 1, (10, d))
+    f1 = lambda x: x[1] + x[0] ** 2 + x[1] ** 2 - np.sqrt(2)  # noqa: E731
+    f2 = lambda x: np.sin(2 * np.pi * x[0]) + np.sin(4 * np.pi * x[0] * x[1])  # noqa: E731
+    data = api.MultiLevel([[api.TrainingDatum(api.Input(*x), float(f1(x))) for x in X1],
+                           [api.TrainingDatum(api.Input(*x), float(f2(x))) for x in X2]])
+    hps = {1: ([0.6, 0.9], 2.0, 1e-9), 2: ([0.2, 0.3], 1.5, 1e-9)}
+    ours = api.MultiLevelGaussianProcess([api.B200GaussianProcess(kernel="Matern52") for _ in range(2)])
+    refs = api.MultiLevelGaussianProcess([api.MogpEmulator(kernel="Matern52") for _ in range(2)])
+    ours.fit(data, hyperparameters=api.MultiLevel({k: api.GaussianProcessHyperparameters(*v) for k, v in hps.items()}))
+    refs.fit(data, hyperparameters=api.MultiLevel({k: api.MogpHyperparameters(*v) for k, v in hps.items()}))
+    x = api.Input(0.5, 0.7)
+    a, b = ours.predict(x), refs.predict(x)
+    assert close(a.estimate, b.estimate) and close(a.variance, b.variance)
+    for level, i in [(1, 0), (1, 7), (2, 3)]:
+        a = api.designers.compute_multi_level_loo_prediction(ours, level, i)
+        b = api.designers.compute_multi_level_loo_prediction(refs, level, i)
+        assert close(a.estimate, b.estimate, rel=1e-7, abs_=1e-8) and close(a.variance, b.variance, rel=1e-7)
+
+
+def test_pei_candidates_matches_reference_peicalculator(api):
+    """B200GaussianProcess.pei_candidates vs the reference's PEICalculator evaluated point
+    by point, including the batch loop's repulsion updates."""
+    g = load_golden("fixed_matern_d3_n40.json")
+    data = _data(api, g)
+    hp = g["hyperparameters"]
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters(hp["corr_length_scales"], hp["process_var"],
+                                                                   hp["nugget"]))
+    domain = api.SimulatorDomain([(0.0, 1.0)] * 3)
+    pei = api.designers.PEICalculator(domain, gp)     # unchanged reference class on our GP
+    Xc = np.random.default_rng(9).uniform(0, 1, (300, 3))
+    rep = np.array([list(x) for x in pei._other_repulsion_points])
+    idx, val, cand = gp.pei_candidates(Xc, rep, batch_size=3)
+    ref_vals = np.array([pei.compute(api.Input(*x)) for x in Xc])
+    chosen = []
+    for _ in range(3):
+        i = int(np.argmax(ref_vals))
+        chosen.append(i)
+        pei.add_repulsion_points([api.Input(*Xc[i])])
+        ref_vals = np.array([pei.compute(api.Input(*x)) for x in Xc])
+    assert idx.tolist() == chosen
+    assert np.allclose(cand.download("pei"), ref_vals, rtol=1e-7, atol=1e-13 * np.max(val))
