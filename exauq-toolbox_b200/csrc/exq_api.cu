@@ -465,7 +465,7 @@ int exq_timer_stop(double* ms) {
 int exq_prof_enable(int mask) {
     REQUIRE_READY();
     if (mask && g.pool.empty()) {
-        g.pool.resize(16384);
+        g.pool.resize(131072);
         for (auto& ev : g.pool) CUDA_TRY(cudaEventCreate(&ev));
     }
     g.prof_mask = (unsigned)mask;

@@ -1,0 +1,208 @@
+"""A single-level design batch over a fixed candidate set, sharded by rank.
+
+This is the reference's ``compute_single_level_loo_samples``
+(exauq/core/designers.py:709-837) with its differential-evolution maximiser
+(exauq/utilities/optimisation.py:14-104) replaced by an arg max over candidates resident in
+HBM, as BASELINE.json's configs describe:
+
+  1. LOO sweep of the GP with its fitted hyperparameters + NES errors   (designers.py:263-272)
+  2. errors GP: MAP estimation with the length-scale lower bounds         (:274-292)
+  3. PEI of the errors GP over the candidates, ``batch_size`` rounds of
+     arg max + repulsion update                                          (:825-835)
+
+Ranks hold the same training data; candidates and optimiser restarts are sharded (one
+process per GPU).  The only exchanges are tiny all-gathers: the best restart, and one
+(value, index, point) triple per rank per batch round.
+"""
+
+from __future__ import annotations
+
+import itertools
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._lib import DeviceCandidates, DeviceGP
+from .gp import run_map_restarts
+from .priors import MapPriors
+
+
+# ---------------------------------------------------------------------------------------
+# host-side geometry (vectorised restatements of O(N * 2^d) Python loops in the reference)
+# ---------------------------------------------------------------------------------------
+def _rows_equal(a: np.ndarray, b: np.ndarray, tol: float = 1e-9) -> np.ndarray:
+    """Input.__eq__ (exauq/core/modelling.py:287-307): every coordinate within rel/abs 1e-9."""
+    return np.all(np.abs(a - b) <= np.maximum(tol * np.maximum(np.abs(a), np.abs(b)), tol), axis=-1)
+
+
+def domain_corners(bounds: Sequence[Sequence[float]]) -> np.ndarray:
+    """SimulatorDomain._define_corners (modelling.py:2142-2151): product of the bounds, duplicates dropped."""
+    pts = np.array(list(itertools.product(*[tuple(b) for b in bounds])), dtype=float)
+    keep = []
+    for i in range(pts.shape[0]):
+        if not any(_rows_equal(pts[i], pts[j]) for j in keep):
+            keep.append(i)
+    return pts[keep]
+
+
+def pseudopoints(X: np.ndarray, bounds: Sequence[Sequence[float]]) -> np.ndarray:
+    """SimulatorDomain.calculate_pseudopoints (modelling.py:2233-2277): for every face of the box
+    the projection of the (first) training input closest to it (closest_boundary_points,
+    :2157-2231; corner inputs skipped, duplicates and corners dropped), then the corners."""
+    X = np.asarray(X, dtype=float)
+    corners = domain_corners(bounds)
+    d = X.shape[1]
+    is_corner = np.zeros(X.shape[0], dtype=bool)
+    for c in corners:
+        is_corner |= _rows_equal(X, c)
+    cand_idx = np.nonzero(~is_corner)[0]
+    out: list[np.ndarray] = []
+    if cand_idx.size:
+        for i in range(d):
+            for bound in (bounds[i][0], bounds[i][1]):
+                dist = np.abs(X[cand_idx, i] - bound)
+                p = X[cand_idx[int(np.argmin(dist))]].copy()
+                p[i] = bound
+                if any(_rows_equal(p, q) for q in out) or np.any(_rows_equal(corners, p)):
+                    continue
+                out.append(p)
+    pts = np.array(out, dtype=float).reshape(-1, d)
+    return np.vstack([pts, corners])
+
+
+def loo_error_raw_bounds(bounds: Sequence[Sequence[float]]):
+    """_compute_loo_error_bounds (designers.py:280-292) mapped to raw parameters as
+    MogpEmulator._compute_raw_param_bounds does (emulators.py:453-485): length scales bounded
+    below by 0.25/sqrt(ln 10) * side, i.e. corr_raw bounded ABOVE; process variance free."""
+    scale = 0.25 / math.sqrt(math.log(10))
+    raw = [(None, -2.0 * math.log(scale * (b[1] - b[0]))) for b in bounds]
+    return tuple(raw) + ((None, None),)
+
+
+# ---------------------------------------------------------------------------------------
+# communication: one process per GPU
+# ---------------------------------------------------------------------------------------
+class SingleComm:
+    rank, size = 0, 1
+
+    def allgather(self, arr: np.ndarray) -> np.ndarray:
+        return np.asarray(arr, dtype=float)[None, ...]
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    """torch.distributed (NCCL over NVLink on GPUs, gloo in CPU tests) for the tiny all-gathers."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self._torch, self._dist = torch, dist
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+
+    def allgather(self, arr: np.ndarray) -> np.ndarray:
+        t = self._torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64), device=self.device)
+        out = self._torch.empty((self.size,) + tuple(t.shape), dtype=t.dtype, device=self.device)
+        self._dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+
+    def barrier(self):
+        self._dist.barrier()
+
+
+def pick_global_best(vals: np.ndarray, idxs: np.ndarray) -> int:
+    """Rank holding the global arg max: largest value, lowest global index on ties, NaN ignored."""
+    vals = np.where(np.isnan(vals), -np.inf, vals)
+    best = np.max(vals)
+    tied = np.nonzero(vals == best)[0]
+    return int(tied[np.argmin(idxs[tied])])
+
+
+# ---------------------------------------------------------------------------------------
+# the design batch
+# ---------------------------------------------------------------------------------------
+def design_batch(
+    X: np.ndarray,
+    y: np.ndarray,
+    kernel: str,
+    corr_length_scales,
+    process_var: float,
+    nugget: float,
+    bounds: Sequence[Sequence[float]],
+    candidates,
+    batch_size: int = 1,
+    n_tries: int = 15,
+    seed: Optional[int] = None,
+    comm=None,
+    candidate_offset: int = 0,
+    gp_factory=DeviceGP,
+    cand_factory=DeviceCandidates,
+    stats: Optional[dict] = None,
+):
+    """New design points for a GP with training data (X, y) and fitted hyperparameters.
+
+    ``candidates`` is this rank's shard (array or device-resident candidate set) whose first
+    row has global index ``candidate_offset``.  Returns ``(points[batch_size, d],
+    global_indices[batch_size], pei_values[batch_size], errors_gp_theta_raw)``; identical on
+    every rank.
+    """
+    comm = comm or SingleComm()
+    X = np.ascontiguousarray(X, dtype=float)
+    y = np.ascontiguousarray(y, dtype=float)
+    d = X.shape[1]
+    stats = stats if stats is not None else {}
+
+    # 1. leave-one-out sweep with the fitted hyperparameters
+    corr_raw = -2.0 * np.log(np.asarray(corr_length_scales, dtype=float))
+    gp = gp_factory(X, y, kernel)
+    gp.fit(corr_raw, process_var, nugget)
+    _, _, nes = gp.loo()
+    if not np.all(np.isfinite(nes)):
+        raise FloatingPointError("non-finite NES error in the leave-one-out sweep")
+
+    # 2. errors GP: MAP estimate, restarts sharded over ranks
+    gp_e = gp_factory(X, nes, kernel)
+    priors = MapPriors(X)
+    if seed is not None:
+        np.random.seed(seed + 7919 * comm.rank)
+    starts = [priors.sample() for _ in range(n_tries)]
+    mstats: dict = {}
+    results = run_map_restarts(gp_e, priors, starts, loo_error_raw_bounds(bounds), 0.0, True, stats=mstats,
+                               return_all=True)
+    done = [r for r in results if r is not None]
+    local = np.full(d + 2, np.inf)
+    if done:
+        k = int(np.argmin([r[0] for r in done]))
+        local[0], local[1:] = done[k][0], done[k][1]
+    gathered = comm.allgather(local)
+    if not np.any(np.isfinite(gathered[:, 0])):
+        raise RuntimeError("GP fitting failed")
+    theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
+    gp_e.fit(theta[:d], float(np.exp(theta[d])), 0.0, True)
+    stats.update(map_batches=mstats.get("batches", 0), map_evals=mstats.get("evals", 0))
+
+    # 3. PEI over this rank's candidates, batch_size rounds of arg max + repulsion update
+    cand = candidates if hasattr(candidates, "pei_eval") else cand_factory(candidates)
+    rep = pseudopoints(X, bounds)
+    cand.pei_eval(gp_e, rep, float(np.max(nes)))
+    pts = np.empty((batch_size, d))
+    gidx = np.empty(batch_size, dtype=np.int64)
+    vals = np.empty(batch_size)
+    if comm.size == 1:
+        li, lv = cand.batch(gp_e, batch_size)
+        for s in range(batch_size):
+            pts[s] = cand.Xc[li[s]]
+        gidx[:], vals[:] = li + candidate_offset, lv
+    else:
+        for s in range(batch_size):
+            i, v = cand.argmax()
+            msg = np.concatenate([[v, float(i + candidate_offset)], cand.Xc[i]])
+            allm = comm.allgather(msg)
+            w = pick_global_best(allm[:, 0], allm[:, 1])
+            vals[s], gidx[s], pts[s] = allm[w, 0], int(allm[w, 1]), allm[w, 2:]
+            cand.add_point(gp_e, pts[s])
+    return pts, gidx, vals, theta

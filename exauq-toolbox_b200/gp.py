@@ -570,14 +570,15 @@ class _Rendezvous:
                 self._flush_locked()
 
 
-def run_map_restarts(dev: DeviceGP, priors: MapPriors, starts, raw_bounds, nugget: float, adaptive: bool,
-                     stats: Optional[dict] = None) -> Optional[np.ndarray]:
+def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, adaptive: bool,
+                     stats: Optional[dict] = None, return_all: bool = False):
     """One scipy L-BFGS-B minimisation per starting point, as the restart loop of
     ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:309-335); each optimiser runs in
     its own thread and all objective/gradient requests of a round are evaluated in one
     batched GPU call.  Restarts that hit a non-positive-definite covariance or a floating
     point overflow are skipped (:332-335).  Returns the raw parameters with the lowest
-    negative log-posterior, or None if every restart failed."""
+    negative log-posterior, or None if every restart failed (``return_all``: the list of
+    ``(value, theta)`` / ``None`` per start instead)."""
     d = dev.d
     rv = _Rendezvous(dev, len(starts), nugget, adaptive)
     out: list[Optional[tuple[float, np.ndarray]]] = [None] * len(starts)
@@ -616,6 +617,8 @@ def run_map_restarts(dev: DeviceGP, priors: MapPriors, starts, raw_bounds, nugge
         t.join()
     if stats is not None:
         stats.update(batches=rv.n_batches, evals=rv.n_evals)
+    if return_all:
+        return out
     done = [o for o in out if o is not None]
     if not done:
         return None
