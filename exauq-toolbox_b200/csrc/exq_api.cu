@@ -209,11 +209,12 @@ namespace {
 template <int AL, int BL>
 int launch_gemm(const GemmArgs& a, int batch, int cls) {
     dim3 grid(a.N / GEMM_BN, a.M / GEMM_BM, batch);
+    if (a.raster > 0) grid = dim3((a.M / GEMM_BM) * (a.N / GEMM_BN), 1, batch);
     // algorithmic flop estimate (triangular k ranges / lower-only halve the work)
     double fl = 2.0 * a.M * (double)a.N * a.K * batch;
-    if (a.krange != KR_FULL) fl *= 0.5;
-    if (a.lower_only && a.krange == KR_FULL) fl *= 0.5;
-    if (a.lower_only && a.krange != KR_FULL) fl *= 2.0 / 3.0;
+    if (a.krange != KR_FULL) fl *= 0.5;                          // triangular operand
+    if (a.lower_only && a.krange == KR_FULL) fl *= 0.5;          // SYRK: n^2 k
+    if (a.lower_only && a.krange != KR_FULL) fl *= 1.0 / 3.0;    // LAUUM: n^3 / 3
     ProfMark m = prof_begin(cls, fl, 0.0);
     gemm_dmma_kernel<AL, BL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(a);
     prof_end(m);
@@ -221,8 +222,8 @@ int launch_gemm(const GemmArgs& a, int batch, int cls) {
 }
 
 int launch_assemble(const AsmArgs& a, int rows_pad, int cols_pad, int batch) {
-    size_t smem = ((size_t)2 * 128 * a.d + (size_t)a.d * ASM_XT_LD + a.d + 2) * sizeof(double);
-    dim3 grid(cols_pad / 128, rows_pad / 128, batch);
+    size_t smem = ((size_t)(128 + ASM_BN) * a.d + (size_t)a.d * ASM_XT_LD + a.d + 2) * sizeof(double);
+    dim3 grid(cols_pad / ASM_BN, rows_pad / 128, batch);
     double entries = (double)rows_pad * cols_pad * batch * (a.sym ? 0.5 : 1.0);
     ProfMark m = prof_begin(EXQ_PROF_ASSEMBLE, entries * (3.0 * a.d + 30.0), entries * 8.0);
     assemble_kernel<<<grid, ASM_THREADS, smem, g.stream>>>(a);
@@ -349,7 +350,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
         ga.A = gp->fit.Linv; ga.B = gp->KcT; ga.C = gp->P;
         ga.lda = Np; ga.ldb = Np; ga.ldc = mc_pad;
         ga.M = Np; ga.N = (int)mc_pad; ga.K = Np;
-        ga.krange = KR_LE_I; ga.lower_only = 0; ga.cmode = C_COLSUMSQ;
+        ga.krange = KR_LE_I; ga.lower_only = 0; ga.cmode = C_COLSUMSQ; ga.raster = 8;
         if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
         FinArgs f{};
         f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = Np / 128;
@@ -813,7 +814,7 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
         if (!rc) rc = solve_vectors(s, gp->y, 0, N);
         if (!rc && grad) rc = lauum(s);
         if (!rc && grad) {
-            size_t smem = ((size_t)128 * d + (size_t)d * ASM_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
+            size_t smem = ((size_t)128 * d + (size_t)d * GRAD_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
             dim3 grid(nt, nt, B);
             ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)B * N * N * 0.5 * (5.0 * d + 40.0), (double)B * N * N * 4.0);
             if (dmax == 8)

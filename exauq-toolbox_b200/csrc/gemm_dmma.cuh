@@ -29,6 +29,11 @@ struct GemmArgs {
     int krange;        // KR_*: restricts the k loop per output tile (triangular operands)
     int lower_only;    // skip tiles strictly above the diagonal
     int cmode;         // C_*
+    int raster;        // 0: blockIdx.x -> column tile, blockIdx.y -> row tile.
+                       // G > 0: 1-D grid over (row tile, column tile); column tiles are taken in
+                       //    groups of G and, inside a group, row tiles heaviest-first.  The G
+                       //    B-operand tiles of a group plus the whole A operand stay in L2, so
+                       //    HBM traffic drops to about the algorithmic bytes.
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16, GEMM_STAGES = 4, GEMM_THREADS = 256;
@@ -63,8 +68,19 @@ template <int AL, int BL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double gemm_smem[];
     // heavy tiles first: with triangular k ranges the work grows with it (or shrinks with jt)
-    int it = (p.krange == KR_LE_I) ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-    int jt = (p.krange == KR_LE_J) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    int it, jt;
+    if (p.raster > 0) {
+        const int nI = p.M / GEMM_BM, nJ = p.N / GEMM_BN, G = p.raster;
+        const int b = blockIdx.x, per_group = G * nI;
+        const int grp = b / per_group, r = b - grp * per_group;
+        const int gw = min(G, nJ - grp * G);
+        const int ir = r / gw;
+        jt = grp * G + (r - ir * gw);
+        it = (p.krange == KR_LE_I) ? (nI - 1 - ir) : ir;
+    } else {
+        it = (p.krange == KR_LE_I) ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+        jt = (p.krange == KR_LE_J) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    }
     if (p.lower_only && jt > it) return;
 
     const int tid = threadIdx.x;

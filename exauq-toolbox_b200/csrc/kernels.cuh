@@ -19,8 +19,10 @@ namespace exq {
 //          (AbstractGaussianProcess.covariance_matrix, exauq/core/modelling.py:1042-1080)
 // Point tiles (128 points x d, contiguous) are staged with one TMA bulk copy each.
 // =====================================================================================
+constexpr int GRAD_XT_LD = 132;
 constexpr int ASM_THREADS = 256;
-constexpr int ASM_XT_LD = 132;
+constexpr int ASM_BN = 64;          // CTA tile: 128 rows x 64 columns, 8 x 4 entries per thread
+constexpr int ASM_XT_LD = ASM_BN + 4;
 
 struct AsmArgs {
     const double* Xi;      // row points  [rows_pad][d]
@@ -33,20 +35,20 @@ struct AsmArgs {
     int scale_sigma2;      // 0: plain correlation (no sigma2, no nugget)
 };
 
-__global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs p) {
+__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(AsmArgs p) {
     const int it = blockIdx.y, jt = blockIdx.x;
-    if (p.sym && jt > it) return;
+    if (p.sym && jt * ASM_BN > it * 128 + 127) return;
     extern __shared__ __align__(16) double asm_smem[];
     const int d = p.d;
     double* Xi_s = asm_smem;                   // [128][d]
-    double* Xj_s = Xi_s + 128 * d;             // [128][d]
-    double* XjT = Xj_s + 128 * d;              // [d][132]
+    double* Xj_s = Xi_s + 128 * d;             // [64][d]
+    double* XjT = Xj_s + ASM_BN * d;           // [d][68]
     double* w_s = XjT + d * ASM_XT_LD;         // [d+2]
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
     const double* Xi = p.Xi + (int64_t)blockIdx.z * p.strideXi + (int64_t)it * 128 * d;
-    const double* Xj = p.Xj + (int64_t)blockIdx.z * p.strideXj + (int64_t)jt * 128 * d;
+    const double* Xj = p.Xj + (int64_t)blockIdx.z * p.strideXj + (int64_t)jt * ASM_BN * d;
     const double* theta = p.theta + (int64_t)blockIdx.z * p.strideTheta;
     double* out = p.out + (int64_t)blockIdx.z * p.strideOut;
 
@@ -56,39 +58,39 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs p) {
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes = 128u * d * sizeof(double);
-        mbar_expect_tx(&bar, 2 * bytes);
-        tma_bulk_g2s(Xi_s, Xi, bytes, &bar);
-        tma_bulk_g2s(Xj_s, Xj, bytes, &bar);
+        const uint32_t bi = 128u * d * sizeof(double), bj = (uint32_t)ASM_BN * d * sizeof(double);
+        mbar_expect_tx(&bar, bi + bj);
+        tma_bulk_g2s(Xi_s, Xi, bi, &bar);
+        tma_bulk_g2s(Xj_s, Xj, bj, &bar);
     }
     if (tid < d + 2) w_s[tid] = theta[tid];
     mbar_wait(&bar, 0);
-    for (int e = tid; e < 128 * d; e += ASM_THREADS) {
+    for (int e = tid; e < ASM_BN * d; e += ASM_THREADS) {
         int pt = e / d, k = e - pt * d;
         XjT[k * ASM_XT_LD + pt] = Xj_s[e];
     }
     __syncthreads();
 
     const int ty = tid >> 4, tx = tid & 15;
-    double acc[8][8];
+    double acc[8][4];
     const bool prod = (p.kernel_id == EXQ_KERNEL_PRODMAT52);
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = prod ? 1.0 : 0.0;
+        for (int b = 0; b < 4; b++) acc[a][b] = prod ? 1.0 : 0.0;
 
     for (int k = 0; k < d; k++) {
         const double w = w_s[k];
-        double xi[8], xj[8];
+        double xi[8], xj[4];
 #pragma unroll
         for (int a = 0; a < 8; a++) xi[a] = Xi_s[(ty * 8 + a) * d + k];
 #pragma unroll
-        for (int b = 0; b < 8; b++) xj[b] = XjT[k * ASM_XT_LD + tx + 16 * b];
+        for (int b = 0; b < 4; b++) xj[b] = XjT[k * ASM_XT_LD + tx + 16 * b];
         if (!prod) {
 #pragma unroll
             for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
+                for (int b = 0; b < 4; b++) {
                     double df = xi[a] - xj[b];
                     acc[a][b] = fma(w * df, df, acc[a][b]);
                 }
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs p) {
 #pragma unroll
             for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
+                for (int b = 0; b < 4; b++) {
                     double df = xi[a] - xj[b];
                     acc[a][b] *= mat52_1d(w * df * df);
                 }
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(ASM_THREADS) assemble_kernel(AsmArgs p) {
     for (int a = 0; a < 8; a++) {
         const int gi = it * 128 + ty * 8 + a;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            const int gj = jt * 128 + tx + 16 * b;
+        for (int b = 0; b < 4; b++) {
+            const int gj = jt * ASM_BN + tx + 16 * b;
             double v;
             if (gi < p.n_i && gj < p.n_j) {
                 double cv = prod ? acc[a][b] : corr_from_r2(p.kernel_id, acc[a][b]);
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
     extern __shared__ __align__(16) double g_smem[];
     double* Xi_s = g_smem;                  // [128][d]
     double* XjT = Xi_s + 128 * d;           // [d][132]
-    double* w_s = XjT + d * ASM_XT_LD;      // [d+2]
+    double* w_s = XjT + d * GRAD_XT_LD;      // [d+2]
     double* ai_s = w_s + (d + 2);           // [128]
     double* aj_s = ai_s + 128;              // [128]
     double* red = aj_s + 128;               // [8][DMAX+2]
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
     for (int e = tid; e < 128 * d; e += 256) {
         int pt = e / d, k = e - pt * d;
         Xi_s[e] = X[(int64_t)(it * 128) * d + e];
-        XjT[k * ASM_XT_LD + pt] = X[(int64_t)(jt * 128) * d + e];
+        XjT[k * GRAD_XT_LD + pt] = X[(int64_t)(jt * 128) * d + e];
     }
     if (tid < d + 2) w_s[tid] = theta[tid];
     if (tid < 128) { ai_s[tid] = alpha[it * 128 + tid]; aj_s[tid] = alpha[jt * 128 + tid]; }
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
 #pragma unroll
             for (int k = 0; k < DMAX; k++) {
                 if (k < d) {
-                    double df = Xi_s[li * d + k] - XjT[k * ASM_XT_LD + lj];
+                    double df = Xi_s[li * d + k] - XjT[k * GRAD_XT_LD + lj];
                     gk[k] = w_s[k] * df * df;
                     r2 += gk[k];
                 } else gk[k] = 0.0;

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import time
 from typing import Optional, Sequence
 
 import numpy as np
@@ -39,6 +40,8 @@ def _rows_equal(a: np.ndarray, b: np.ndarray, tol: float = 1e-9) -> np.ndarray:
 def domain_corners(bounds: Sequence[Sequence[float]]) -> np.ndarray:
     """SimulatorDomain._define_corners (modelling.py:2142-2151): product of the bounds, duplicates dropped."""
     pts = np.array(list(itertools.product(*[tuple(b) for b in bounds])), dtype=float)
+    if all(abs(b[1] - b[0]) > 1e-9 * max(1.0, abs(b[0]), abs(b[1])) for b in bounds):
+        return pts                      # no degenerate side: the 2^d corners are distinct
     keep = []
     for i in range(pts.shape[0]):
         if not any(_rows_equal(pts[i], pts[j]) for j in keep):
@@ -53,9 +56,14 @@ def pseudopoints(X: np.ndarray, bounds: Sequence[Sequence[float]]) -> np.ndarray
     X = np.asarray(X, dtype=float)
     corners = domain_corners(bounds)
     d = X.shape[1]
-    is_corner = np.zeros(X.shape[0], dtype=bool)
-    for c in corners:
-        is_corner |= _rows_equal(X, c)
+    lo = np.array([b[0] for b in bounds], dtype=float)
+    hi = np.array([b[1] for b in bounds], dtype=float)
+
+    def _close(a, b, tol=1e-9):
+        return np.abs(a - b) <= np.maximum(tol * np.maximum(np.abs(a), np.abs(b)), tol)
+
+    # a point equals some corner iff every coordinate sits on one of its two bounds
+    is_corner = np.all(_close(X, lo) | _close(X, hi), axis=1)
     cand_idx = np.nonzero(~is_corner)[0]
     out: list[np.ndarray] = []
     if cand_idx.size:
@@ -64,7 +72,7 @@ def pseudopoints(X: np.ndarray, bounds: Sequence[Sequence[float]]) -> np.ndarray
                 dist = np.abs(X[cand_idx, i] - bound)
                 p = X[cand_idx[int(np.argmin(dist))]].copy()
                 p[i] = bound
-                if any(_rows_equal(p, q) for q in out) or np.any(_rows_equal(corners, p)):
+                if (out and np.any(_rows_equal(np.array(out), p))) or np.all(_close(p, lo) | _close(p, hi)):
                     continue
                 out.append(p)
     pts = np.array(out, dtype=float).reshape(-1, d)
@@ -156,6 +164,7 @@ def design_batch(
     d = X.shape[1]
     stats = stats if stats is not None else {}
 
+    t0 = time.perf_counter()
     # 1. leave-one-out sweep with the fitted hyperparameters
     corr_raw = -2.0 * np.log(np.asarray(corr_length_scales, dtype=float))
     gp = gp_factory(X, y, kernel)
@@ -164,6 +173,7 @@ def design_batch(
     if not np.all(np.isfinite(nes)):
         raise FloatingPointError("non-finite NES error in the leave-one-out sweep")
 
+    t1 = time.perf_counter()
     # 2. errors GP: MAP estimate, restarts sharded over ranks
     gp_e = gp_factory(X, nes, kernel)
     priors = MapPriors(X)
@@ -183,7 +193,9 @@ def design_batch(
         raise RuntimeError("GP fitting failed")
     theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
     gp_e.fit(theta[:d], float(np.exp(theta[d])), 0.0, True)
-    stats.update(map_batches=mstats.get("batches", 0), map_evals=mstats.get("evals", 0))
+    t2 = time.perf_counter()
+    stats.update(map_batches=mstats.get("batches", 0), map_evals=mstats.get("evals", 0),
+                 map_gpu_s=mstats.get("gpu_s", 0.0))
 
     # 3. PEI over this rank's candidates, batch_size rounds of arg max + repulsion update
     cand = candidates if hasattr(candidates, "pei_eval") else cand_factory(candidates)
@@ -205,4 +217,6 @@ def design_batch(
             w = pick_global_best(allm[:, 0], allm[:, 1])
             vals[s], gidx[s], pts[s] = allm[w, 0], int(allm[w, 1]), allm[w, 2:]
             cand.add_point(gp_e, pts[s])
+    t3 = time.perf_counter()
+    stats.update(loo_s=t1 - t0, map_s=t2 - t1, pei_s=t3 - t2)
     return pts, gidx, vals, theta

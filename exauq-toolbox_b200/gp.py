@@ -26,6 +26,7 @@ import copy
 import itertools
 import math
 import threading
+import time
 from collections.abc import Collection, Sequence
 from numbers import Real
 from typing import Any, Optional
@@ -538,11 +539,13 @@ class _Rendezvous:
         self.results: dict[int, tuple] = {}
         self.n_batches = 0
         self.n_evals = 0
+        self.gpu_s = 0.0
 
     def _flush_locked(self):
         keys = sorted(self.pending)
         thetas = np.array([self.pending[k] for k in keys])
         self.pending.clear()
+        t0 = time.perf_counter()
         try:
             val, grad, info, _ = self.dev.logpost_batch(thetas, self.nugget, self.adaptive)
             for i, k in enumerate(keys):
@@ -550,6 +553,7 @@ class _Rendezvous:
         except Exception as exc:  # propagate to every waiting worker
             for k in keys:
                 self.results[k] = (None, None, -1, exc)
+        self.gpu_s += time.perf_counter() - t0
         self.n_batches += 1
         self.n_evals += len(keys)
         self.cv.notify_all()
@@ -616,7 +620,7 @@ def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, 
     for t in threads:
         t.join()
     if stats is not None:
-        stats.update(batches=rv.n_batches, evals=rv.n_evals)
+        stats.update(batches=rv.n_batches, evals=rv.n_evals, gpu_s=rv.gpu_s)
     if return_all:
         return out
     done = [o for o in out if o is not None]
