@@ -113,10 +113,11 @@ class TorchComm:
         self.device = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
 
     def allgather(self, arr: np.ndarray) -> np.ndarray:
-        t = self._torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64), device=self.device)
-        out = self._torch.empty((self.size,) + tuple(t.shape), dtype=t.dtype, device=self.device)
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        t = self._torch.as_tensor(arr.reshape(-1), device=self.device)
+        out = self._torch.empty(self.size * t.numel(), dtype=t.dtype, device=self.device)
         self._dist.all_gather_into_tensor(out, t)
-        return out.cpu().numpy()
+        return out.cpu().numpy().reshape((self.size,) + arr.shape)
 
     def barrier(self):
         self._dist.barrier()

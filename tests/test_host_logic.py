@@ -1,0 +1,149 @@
+"""Host-side logic that needs no GPU: duplicate detection, priors, bounds, pseudopoints, the
+MAP restart driver's batching, the drop-in class's argument validation, and the design batch
+on one rank (with the oracle standing in for the device)."""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, needs_exauq
+from fakes import OracleCandidates, OracleGP
+
+
+def test_find_duplicate_rows_matches_brute_force():
+    pytest.importorskip("exauq")
+    from exauq_toolbox_b200.gp import find_duplicate_rows
+
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, (300, 3))
+    assert find_duplicate_rows(X) is None
+    X[217] = X[40] + np.array([5e-10, -5e-10, 0.0])       # within abs tolerance 1e-9
+    assert find_duplicate_rows(X) == (40, 217)
+    X[217, 1] += 1e-6
+    assert find_duplicate_rows(X) is None
+    Y = np.array([[1e6, 2.0], [1e6 * (1 + 5e-10), 2.0]])   # within relative tolerance
+    assert find_duplicate_rows(Y) == (0, 1)
+
+
+@needs_exauq
+def test_pseudopoints_and_bounds_match_reference():
+    from exauq.core.designers import _compute_loo_error_bounds
+    from exauq.core.modelling import GaussianProcessHyperparameters as HP
+    from exauq.core.modelling import Input, SimulatorDomain
+
+    from exauq_toolbox_b200.design import loo_error_raw_bounds, pseudopoints
+
+    rng = np.random.default_rng(1)
+    for bounds, n in [([(0, 1), (-0.5, 1.5)], 8), ([(0, 1)] * 3, 20), ([(0, 2), (1, 3), (0, 1), (-1, 1)], 30)]:
+        lo, hi = np.array([b[0] for b in bounds], float), np.array([b[1] for b in bounds], float)
+        X = lo + (hi - lo) * rng.uniform(0, 1, (n, len(bounds)))
+        X[0] = lo                      # a corner input must be skipped (modelling.py:2212)
+        X[1, 0] = lo[0]                # already on a face
+        dom = SimulatorDomain(bounds)
+        ref = np.array([list(p) for p in dom.calculate_pseudopoints([Input(*r) for r in X])])
+        assert np.array_equal(ref, pseudopoints(X, bounds))
+        # raw bounds: (None, -2 ln(lower)) per length scale, (None, None) for the variance
+        raw = loo_error_raw_bounds(bounds)
+        for (lo_b, _), (rlo, rhi) in zip(_compute_loo_error_bounds(dom)[:-1], raw[:-1]):
+            assert rlo is None and np.isclose(rhi, HP.transform_corr(lo_b))
+        assert raw[-1] == (None, None)
+
+
+def test_map_driver_batches_and_matches_sequential_reference_fit():
+    """run_map_restarts = the restart loop of exauq/utilities/mogp_fitting.py:309-346: same
+    starting points (same numpy seed), same optimiser => same optimum as the oracle's
+    sequential fit_GP_MAP; evaluations arrive in batches."""
+    pytest.importorskip("exauq")
+    import mogp_emulator as mogp
+
+    from exauq_toolbox_b200.gp import run_map_restarts
+    from exauq_toolbox_b200.priors import MapPriors
+
+    g = load_golden("fixed_matern_d3_n40.json")
+    X, y = np.array(g["X"]), np.array(g["y"])
+    np.random.seed(3)
+    ref = mogp.fit_GP_MAP(mogp.GaussianProcess(X, y, kernel="Matern52"), n_tries=6)
+    np.seterr(all="warn")
+    pri = MapPriors(X)
+    np.random.seed(3)
+    starts = [pri.sample() for _ in range(6)]
+    dev = OracleGP(X, y, "Matern52")
+    stats = {}
+    best = run_map_restarts(dev, pri, starts, None, 0.0, True, stats=stats)
+    assert np.allclose(best, ref.theta.get_data(), rtol=1e-6, atol=1e-6)
+    assert stats["evals"] > stats["batches"] >= 1
+    assert dev.n_batches == stats["batches"]
+    # every restart failing => None (the caller raises RuntimeError("GP fitting failed"))
+
+    class Broken(OracleGP):
+        def logpost_batch(self, theta_raw, nugget=0.0, adaptive=False, want_grad=True):
+            R = np.atleast_2d(theta_raw).shape[0]
+            return np.full(R, np.nan), np.full((R, self.d + 1), np.nan), np.ones(R, dtype=np.int32), np.zeros(R)
+
+    assert run_map_restarts(Broken(X, y, "Matern52"), pri, starts[:2], None, 0.0, True) is None
+
+
+@needs_exauq
+def test_dropin_argument_validation_without_gpu():
+    """Checks that run before any device call mirror MogpEmulator (exauq/core/emulators.py:129-190,
+    268-282, 350-395, 466-468, 527-544, 633-641)."""
+    from exauq.core.modelling import AbstractGaussianProcess, Input, TrainingDatum
+
+    from exauq_toolbox_b200.gp import B200GaussianProcess
+
+    with pytest.raises(ValueError, match="not a supported kernel function"):
+        B200GaussianProcess(kernel="Cubic")
+    with pytest.raises(RuntimeError):
+        B200GaussianProcess(foo=1)
+    gp = B200GaussianProcess(kernel="Matern52", inputs=[[1.0]], targets=[2.0])   # inputs/targets ignored
+    assert isinstance(gp, AbstractGaussianProcess)
+    assert gp.training_data == () and gp.fit_hyperparameters is None and gp.kinv.size == 0
+    assert gp.fit([]) is None and gp.fit(None) is None and gp.training_data == ()
+    with pytest.raises(TypeError, match="finite collection of TrainingDatum"):
+        gp.fit([1, 2, 3])
+    data = [TrainingDatum(Input(0.1, 0.2), 1.0), TrainingDatum(Input(0.3, 0.4), 2.0)]
+    with pytest.raises(TypeError, match="Expected 'hyperparameters' to be None or of type"):
+        gp.fit(data, hyperparameters=(1.0, 2.0))
+    with pytest.raises(ValueError, match="not unique within tolerance"):
+        gp.fit(data + [TrainingDatum(Input(0.1, 0.2 + 1e-10), 3.0)])
+    with pytest.raises(ValueError, match="Invalid bound"):
+        gp.fit(data, hyperparameter_bounds=[(2.0, 1.0), (None, None), (None, None)])
+    with pytest.raises(TypeError, match="Invalid bound"):
+        gp.fit(data, hyperparameter_bounds=[("a", 1.0), (None, None), (None, None)])
+    with pytest.raises(ValueError, match="Upper bounds must be positive numbers"):
+        B200GaussianProcess._compute_raw_param_bounds([(None, -1.0), (None, None)])
+    raw = B200GaussianProcess._compute_raw_param_bounds([(0.5, 2.0), (None, 3.0)])
+    assert np.allclose(raw[0], (-2 * np.log(2.0), -2 * np.log(0.5))) and raw[1][0] is None
+    with pytest.raises(TypeError):
+        gp.predict([0.1, 0.2])
+    with pytest.raises(RuntimeError, match="has not been trained"):
+        gp.predict(Input(0.1, 0.2))
+    assert gp.correlation([], [Input(1.0)]).size == 0
+    with pytest.raises(TypeError):
+        gp.correlation(1, 2)
+    with pytest.raises(TypeError):
+        gp.correlation([1.0], [Input(1.0)])
+    with pytest.raises(AssertionError):
+        gp.correlation([Input(1.0)], [Input(1.0)])
+    assert gp.covariance_matrix([Input(1.0, 2.0)]).size == 0
+
+
+def test_design_batch_single_rank_on_oracle_device():
+    """design.design_batch end to end on one rank with the oracle as the device: the chosen
+    candidates are exactly the oracle's PEI batch arg max for the fitted errors GP."""
+    pytest.importorskip("exauq")
+    from oracle import gp_oracle as orc
+
+    from exauq_toolbox_b200.design import design_batch, pseudopoints
+
+    X, y = orc.synthetic_problem(40, 2)
+    Xc = orc.synthetic_candidates(400, 2)
+    bounds = [(0.0, 1.0)] * 2
+    stats = {}
+    pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5, 0.5], 1.7, 0.0, bounds, Xc, batch_size=3, n_tries=4,
+                                          seed=5, gp_factory=OracleGP, cand_factory=OracleCandidates, stats=stats)
+    assert len(set(gidx.tolist())) == 3 and np.allclose(pts, Xc[gidx])
+    _, _, nes = OracleGP(X, y, "Matern52").fit(np.full(2, -2 * np.log(0.5)), 1.7, 0.0).loo()
+    ge = orc.fit(X, nes, "Matern52", theta[:2], float(np.exp(theta[2])), "adaptive")
+    oi, ov, _ = orc.pei_batch_argmax(ge, "Matern52", Xc, pseudopoints(X, bounds), float(nes.max()), 3)
+    assert gidx.tolist() == oi.tolist() and np.allclose(vals, ov, rtol=1e-10)
+    assert stats["map_evals"] > 0

@@ -1,0 +1,84 @@
+"""World-size-2 run of the sharded design batch on CPU (gloo), the oracle standing in for the
+device: both ranks must agree on the chosen points, and they must equal the single-rank result
+over the concatenated candidate set."""
+
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "baseline", "_ref"), os.path.join(ROOT, "tests")]
+import torch.distributed as dist
+from fakes import OracleCandidates, OracleGP
+from oracle import gp_oracle as orc
+from exauq_toolbox_b200.design import TorchComm, design_batch
+dist.init_process_group("gloo")
+comm = TorchComm()
+X, y = orc.synthetic_problem(40, 2)
+Xall = orc.synthetic_candidates(600, 2)
+shard = Xall[comm.rank * 300:(comm.rank + 1) * 300]
+# identical restarts on both ranks so that the fitted errors GP does not depend on the sharding
+class SameSeed:
+    rank, size = 0, comm.size
+    allgather, barrier = comm.allgather, comm.barrier
+pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5, 0.5], 1.7, 0.0, [(0.0, 1.0)] * 2, shard, batch_size=4,
+                                      n_tries=3, seed=5, comm=SameSeed(), candidate_offset=comm.rank * 300,
+                                      gp_factory=OracleGP, cand_factory=OracleCandidates)
+json.dump({"pts": pts.tolist(), "gidx": gidx.tolist(), "vals": vals.tolist(), "theta": theta.tolist()},
+          open(os.path.join(OUT, f"rank{comm.rank}.json"), "w"))
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_two_ranks_agree_with_single_rank(tmp_path):
+    pytest.importorskip("torch")
+    pytest.importorskip("exauq")
+    script = tmp_path / "worker.py"
+    script.write_text(f"ROOT = {ROOT!r}\nOUT = {str(tmp_path)!r}\n" + WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    import json
+
+    r0 = json.load(open(tmp_path / "rank0.json"))
+    r1 = json.load(open(tmp_path / "rank1.json"))
+    assert r0["gidx"] == r1["gidx"] and np.allclose(r0["pts"], r1["pts"]) and np.allclose(r0["theta"], r1["theta"])
+    assert any(i >= 300 for i in r0["gidx"]) or any(i < 300 for i in r0["gidx"])
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fakes import OracleCandidates, OracleGP
+    from oracle import gp_oracle as orc
+
+    from exauq_toolbox_b200.design import design_batch
+
+    X, y = orc.synthetic_problem(40, 2)
+    Xall = orc.synthetic_candidates(600, 2)
+    pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5, 0.5], 1.7, 0.0, [(0.0, 1.0)] * 2, Xall, batch_size=4,
+                                          n_tries=3, seed=5, gp_factory=OracleGP, cand_factory=OracleCandidates)
+    assert gidx.tolist() == r0["gidx"]
+    assert np.allclose(vals, r0["vals"], rtol=1e-9) and np.allclose(pts, r0["pts"])
+
+
+def test_pick_global_best_ties_and_nans():
+    pytest.importorskip("exauq")
+    from exauq_toolbox_b200.design import pick_global_best
+
+    assert pick_global_best(np.array([1.0, 3.0, 3.0]), np.array([5.0, 9.0, 7.0])) == 2   # tie -> lowest index
+    assert pick_global_best(np.array([np.nan, 0.5]), np.array([0.0, 4.0])) == 1
+    assert pick_global_best(np.array([0.0, 0.0]), np.array([300.0, 0.0])) == 1
