@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libexauq_b200.so")
+LIB_PATH = os.environ.get("EXQ_LIB", os.path.join(_HERE, "libexauq_b200.so"))  # EXQ_LIB: kernel-variant experiments
 
 EXQ_OK, EXQ_ERR_ARG, EXQ_ERR_CUDA, EXQ_ERR_STATE, EXQ_NOT_PD = 0, -1, -2, -3, 1
 KERNEL_IDS = {"Matern52": 0, "SquaredExponential": 1, "ProductMat52": 2}

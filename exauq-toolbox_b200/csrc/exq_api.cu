@@ -60,6 +60,7 @@ int fail(int code, const std::string& msg) {
 #define REQUIRE_READY()                                                               \
     do {                                                                              \
         if (!g.ready) return fail(EXQ_ERR_CUDA, "exq_init has not succeeded (no GPU?)"); \
+        cudaSetDevice(g.device); /* the calling host thread may be new (per-thread current device) */ \
     } while (0)
 
 inline int pad128(int64_t n) { return (int)(((n + 127) / 128) * 128); }
@@ -102,12 +103,16 @@ int check_launch(const char* what) {
 
 int set_kernel_attrs() {
     if (g.attrs_set) return EXQ_OK;
-    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_K, LAYOUT_K>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_K, LAYOUT_MN>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<LAYOUT_MN, LAYOUT_MN>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+#define EXQ_SET_GEMM_ATTR(AL, BL, BM)                                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<AL, BL, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  GemmCfg<BM>::SMEM_BYTES))
+    EXQ_SET_GEMM_ATTR(LAYOUT_K, LAYOUT_K, 128);
+    EXQ_SET_GEMM_ATTR(LAYOUT_K, LAYOUT_K, 64);
+    EXQ_SET_GEMM_ATTR(LAYOUT_K, LAYOUT_MN, 128);
+    EXQ_SET_GEMM_ATTR(LAYOUT_K, LAYOUT_MN, 64);
+    EXQ_SET_GEMM_ATTR(LAYOUT_MN, LAYOUT_MN, 128);
+    EXQ_SET_GEMM_ATTR(LAYOUT_MN, LAYOUT_MN, 64);
+#undef EXQ_SET_GEMM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   LEAF_SMEM_BYTES));
     const int big = 220 * 1024;
@@ -206,19 +211,30 @@ namespace {
 // -------------------------------------------------------------------------------------
 // kernel launch helpers
 // -------------------------------------------------------------------------------------
+template <int AL, int BL, int BM>
+int launch_gemm_bm(const GemmArgs& a, int batch, int cls, double fl) {
+    using Cfg = GemmCfg<BM>;
+    dim3 grid(a.N / GEMM_BN, a.M / BM, batch);
+    if (a.raster > 0) grid = dim3((a.M / BM) * (a.N / GEMM_BN), 1, batch);
+    ProfMark m = prof_begin(cls, fl, 0.0);
+    gemm_dmma_kernel<AL, BL, BM><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, g.stream>>>(a);
+    prof_end(m);
+    return check_launch("gemm_dmma_kernel");
+}
+
+// Row tile 128 (1 CTA/SM) when there are enough tiles to fill the chip, else 64 (twice the CTAs,
+// 2 per SM) so that the small GEMMs low in the recursion spread over more SMs.
 template <int AL, int BL>
 int launch_gemm(const GemmArgs& a, int batch, int cls) {
-    dim3 grid(a.N / GEMM_BN, a.M / GEMM_BM, batch);
-    if (a.raster > 0) grid = dim3((a.M / GEMM_BM) * (a.N / GEMM_BN), 1, batch);
-    // algorithmic flop estimate (triangular k ranges / lower-only halve the work)
+    // algorithmic flops (triangular k ranges / lower-only halve the work)
     double fl = 2.0 * a.M * (double)a.N * a.K * batch;
     if (a.krange != KR_FULL) fl *= 0.5;                          // triangular operand
     if (a.lower_only && a.krange == KR_FULL) fl *= 0.5;          // SYRK: n^2 k
     if (a.lower_only && a.krange != KR_FULL) fl *= 1.0 / 3.0;    // LAUUM: n^3 / 3
-    ProfMark m = prof_begin(cls, fl, 0.0);
-    gemm_dmma_kernel<AL, BL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, g.stream>>>(a);
-    prof_end(m);
-    return check_launch("gemm_dmma_kernel");
+    double tiles128 = (double)(a.M / 128) * (a.N / 128) * batch * (a.lower_only ? 0.5 : 1.0);
+    if (a.cmode != C_COLSUMSQ && tiles128 < 2.0 * std::max(1, g.sm_count))
+        return launch_gemm_bm<AL, BL, 64>(a, batch, cls, fl);
+    return launch_gemm_bm<AL, BL, 128>(a, batch, cls, fl);
 }
 
 int launch_assemble(const AsmArgs& a, int rows_pad, int cols_pad, int batch) {
