@@ -357,6 +357,10 @@ def run_b200(a):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (NCCL banner, ...) print to fd 1
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -16,6 +16,13 @@
 
 namespace exq {
 
+#ifdef EXQ_LEAF_PROFILE
+__device__ long long leaf_prof[64];
+#define LEAF_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) leaf_prof[i] += clock64() - t_prev; t_prev = clock64(); } while (0)
+#else
+#define LEAF_TICK(i) do { } while (0)
+#endif
+
 constexpr int LEAF_N = 128, LEAF_LD = 132, LEAF_NBLK = 16, LEAF_THREADS = 256;
 constexpr int LEAF_SLOTS = 17;        // 136 tiles / 8 warps
 constexpr int LEAF_XD_LD = 12;
@@ -39,6 +46,9 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
     double* A = Aall + (int64_t)blockIdx.x * strideA + (int64_t)r0 * ld + r0;
     double* Li = Linvall + (int64_t)blockIdx.x * strideL + (int64_t)r0 * ld + r0;
 
+#ifdef EXQ_LEAF_PROFILE
+    long long t_prev = clock64();
+#endif
     // ---- tile ownership -------------------------------------------------------------
     int tb[LEAF_SLOTS];       // (bi << 8) | bj, or -1
     double c[LEAF_SLOTS][2];
@@ -62,40 +72,53 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
         }
     }
     __syncthreads();
+    LEAF_TICK(0);
 
     // ================= phase 1: Cholesky =================================================
     for (int p = 0; p < LEAF_NBLK; p++) {
         const int j0 = 8 * p;
-        // (a) 8 x 8 diagonal block, warp 0 (lanes >= 8 shadow lanes 0..7)
+        // (a) 8 x 8 diagonal block, warp 0.  Every lane factors the whole block redundantly in
+        // registers (36 broadcast loads, no shuffles on the 8-pivot dependency chain).
         if (warp == 0) {
-            const int r = lane & 7;
-            double a[8];
+            double a[8][8];
 #pragma unroll
-            for (int cc = 0; cc < 8; cc++) a[cc] = S[(j0 + r) * LEAF_LD + j0 + cc];
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int cc = 0; cc <= r; cc++) a[r][cc] = S[(j0 + r) * LEAF_LD + j0 + cc];
+            double ri[8];
+            bool bad = false;
 #pragma unroll
             for (int cc = 0; cc < 8; cc++) {
-                double d = __shfl_sync(0xffffffffu, a[cc], cc);
-                double ri = rsqrt(d);
-                double l = d * ri;
-                if (r == cc) a[cc] = l;
-                else if (r > cc) a[cc] *= ri;
+                const double d = a[cc][cc];
+                bad = bad || !(d > 0.0) || !(d < 1.0e300);
+                ri[cc] = rsqrt(d);
+                a[cc][cc] = d * ri[cc];
 #pragma unroll
-                for (int c2 = cc + 1; c2 < 8; c2++) {
-                    double lc = __shfl_sync(0xffffffffu, a[cc], c2);
-                    if (r >= c2) a[c2] -= a[cc] * lc;
-                }
-                if (lane == 0) {
-                    rinv[j0 + cc] = ri;
-                    if (!(d > 0.0) || !(d < 1.0e300)) atomicCAS(info + blockIdx.x, 0, r0 + j0 + cc + 1);
-                }
+                for (int r = cc + 1; r < 8; r++) a[r][cc] *= ri[cc];
+#pragma unroll
+                for (int c2 = cc + 1; c2 < 8; c2++)
+#pragma unroll
+                    for (int r = c2; r < 8; r++) a[r][c2] -= a[r][cc] * a[c2][cc];
             }
             if (lane < 8) {
 #pragma unroll
-                for (int cc = 0; cc < 8; cc++)
-                    if (cc <= r) S[(j0 + r) * LEAF_LD + j0 + cc] = a[cc];
+                for (int r = 0; r < 8; r++)
+                    if (r == lane) {
+#pragma unroll
+                        for (int cc = 0; cc <= r; cc++) S[(j0 + r) * LEAF_LD + j0 + cc] = a[r][cc];
+                        rinv[j0 + r] = ri[r];
+                    }
+            }
+            if (lane == 0 && bad) {
+                int first = 0;
+#pragma unroll
+                for (int cc = 7; cc >= 0; cc--)
+                    if (!(a[cc][cc] > 0.0) || !(a[cc][cc] < 1.0e300) || !(ri[cc] == ri[cc])) first = cc;
+                atomicCAS(info + blockIdx.x, 0, r0 + j0 + first + 1);
             }
         }
         __syncthreads();
+        LEAF_TICK(1);
         // (b) rows below the diagonal block: forward substitution with L11; warp 7 inverts L11
         {
             const int r = j0 + 8 + tid;
@@ -130,6 +153,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
             }
         }
         __syncthreads();
+        LEAF_TICK(2);
         // (c) rank-8 update of every trailing tile, in registers
 #pragma unroll
         for (int s = 0; s < LEAF_SLOTS; s++) {
@@ -149,6 +173,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
             }
         }
         __syncthreads();
+        LEAF_TICK(3);
     }
 
     // ================= phase 2: Linv = L^-1 ==============================================
@@ -179,6 +204,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
             __syncwarp();
         }
         __syncthreads();
+        LEAF_TICK(4);
         // (2) Y_ij += L_ik X_kj for i > k >= j
 #pragma unroll
         for (int s = 0; s < LEAF_SLOTS; s++) {
@@ -198,6 +224,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
             dmma884(c[s][0], c[s][1], a0, b0);
             dmma884(c[s][0], c[s][1], a1, b1);
         }
+        LEAF_TICK(5);
     }
     __syncthreads();
 
@@ -211,6 +238,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
         else if (bc == br) v = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7)];
         Li[(int64_t)r * ld + cc] = v;
     }
+    LEAF_TICK(6);
 }
 
 }  // namespace exq
