@@ -43,6 +43,10 @@ struct Ctx {
     size_t pool_used = 0;
     ProfClass prof[EXQ_PROF_NCLASS];
     bool attrs_set = false;
+    // prediction scratch shared by all GP handles (one stream => no overlap): covariance chunk
+    // KcT[chunk][Np] and the partial column sums P[Np/128][chunk]
+    double *KcT = nullptr, *P = nullptr;
+    size_t kct_elems = 0, p_elems = 0;
 } g;
 
 int fail(int code, const std::string& msg) {
@@ -149,9 +153,45 @@ void sys_free(Sys& s) {
     s = Sys();
 }
 
+// Freed workspaces are parked here and handed back to the next request of the same shape: a
+// design batch creates and destroys several GP handles per step, and cudaMalloc / cudaFree of
+// multi-GB buffers would otherwise cost more than the LOO sweep itself.
+std::vector<Sys> g_sys_pool;
+const size_t SYS_POOL_LIMIT_BYTES = (size_t)48 << 30;
+
+size_t sys_bytes(const Sys& s) {
+    return (size_t)s.B * s.sq() * sizeof(double) * (s.W ? 3 : 2);
+}
+
+void sys_release(Sys& s) {
+    if (!s.A) { s = Sys(); return; }
+    size_t held = 0;
+    for (auto& q : g_sys_pool) held += sys_bytes(q);
+    if (held + sys_bytes(s) <= SYS_POOL_LIMIT_BYTES && g_sys_pool.size() < 16) {
+        g_sys_pool.push_back(s);
+        s = Sys();
+    } else {
+        sys_free(s);
+    }
+}
+
+void sys_pool_clear() {
+    for (auto& q : g_sys_pool) sys_free(q);
+    g_sys_pool.clear();
+}
+
 int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
     if (s.B >= B && s.N == N && s.d == d && (!need_w || s.W) && (!own_data || s.Xb)) return EXQ_OK;
-    sys_free(s);
+    sys_release(s);
+    for (size_t i = 0; i < g_sys_pool.size(); i++) {
+        Sys& q = g_sys_pool[i];
+        if (q.B >= B && q.B <= 2 * B && q.Np == pad128(N) && q.d == d && (!need_w || q.W) && (!own_data || q.Xb)) {
+            s = q;
+            s.N = N;
+            g_sys_pool.erase(g_sys_pool.begin() + i);
+            return EXQ_OK;
+        }
+    }
     s.B = B; s.N = N; s.Np = pad128(N); s.d = d;
     size_t mat = (size_t)B * s.sq() * sizeof(double);
     CUDA_TRY(cudaMalloc(&s.A, mat));
@@ -190,7 +230,7 @@ struct exq_gp_s {
     std::vector<double> corr_raw;
     Sys batch;                              // MLE restarts / LOO refits
     // prediction scratch
-    double *KcT = nullptr, *P = nullptr, *Xchunk = nullptr;
+    double *KcT = nullptr, *P = nullptr;   // views of the global scratch
     int64_t chunk = 0;
     double* rep = nullptr;
     int rep_cap = 0;
@@ -327,13 +367,21 @@ int assemble_sym(Sys& s, const double* X, int64_t strideX, int nvalid, int kerne
 }
 
 int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
-    if (gp->chunk >= want_chunk) return EXQ_OK;
-    cudaFree(gp->KcT); cudaFree(gp->P); cudaFree(gp->Xchunk);
-    gp->KcT = gp->P = gp->Xchunk = nullptr;
-    gp->chunk = 0;
-    CUDA_TRY(cudaMalloc(&gp->KcT, (size_t)want_chunk * gp->Np * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&gp->P, (size_t)(gp->Np / 128) * want_chunk * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&gp->Xchunk, (size_t)want_chunk * gp->d * sizeof(double)));
+    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 128) * want_chunk;
+    if (g.kct_elems < need_k) {
+        cudaFree(g.KcT);
+        g.KcT = nullptr; g.kct_elems = 0;
+        CUDA_TRY(cudaMalloc(&g.KcT, need_k * sizeof(double)));
+        g.kct_elems = need_k;
+    }
+    if (g.p_elems < need_p) {
+        cudaFree(g.P);
+        g.P = nullptr; g.p_elems = 0;
+        CUDA_TRY(cudaMalloc(&g.P, need_p * sizeof(double)));
+        g.p_elems = need_p;
+    }
+    gp->KcT = g.KcT;
+    gp->P = g.P;
     gp->chunk = want_chunk;
     return EXQ_OK;
 }
@@ -353,7 +401,6 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
     int64_t chunk = default_chunk(gp, Mpad);
     int rc = ensure_pred_scratch(gp, chunk);
     if (rc) return rc;
-    chunk = std::min<int64_t>(gp->chunk, Mpad);
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc_pad = std::min(chunk, Mpad - c0);
         const int64_t mc = std::min(mc_pad, M - c0);
@@ -452,6 +499,8 @@ int exq_init(int device) {
 int exq_shutdown(void) {
     if (!g.ready) return EXQ_OK;
     cudaStreamSynchronize(g.stream);
+    sys_pool_clear();
+    cudaFree(g.KcT); cudaFree(g.P);
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
     cudaEventDestroy(g.t0);
@@ -589,9 +638,9 @@ int exq_gp_create(int64_t N, int d, const double* X, const double* y, int kernel
 int exq_gp_destroy(exq_gp_t gp) {
     if (!gp) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
-    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->KcT); cudaFree(gp->P); cudaFree(gp->Xchunk); cudaFree(gp->rep);
-    sys_free(gp->fit);
-    sys_free(gp->batch);
+    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep);
+    sys_release(gp->fit);
+    sys_release(gp->batch);
     delete gp;
     return EXQ_OK;
 }
@@ -766,7 +815,7 @@ int exq_gp_kinv(exq_gp_t gp, double* out) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
         if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_kinv: ") + cudaGetErrorString(e));
     }
-    sys_free(tmp);
+    sys_release(tmp);
     if (rc) return rc;
     for (int i = 0; i < N; i++)   // mirror the lower triangle
         for (int j = i + 1; j < N; j++) out[(size_t)i * N + j] = out[(size_t)j * N + i];

@@ -132,6 +132,68 @@ def pick_global_best(vals: np.ndarray, idxs: np.ndarray) -> int:
 
 
 # ---------------------------------------------------------------------------------------
+# shared steps
+# ---------------------------------------------------------------------------------------
+def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats):
+    """MAP fit of a GP to NES errors with the LOO length-scale bounds, restarts sharded over
+    ranks; every rank ends with the same fitted GP (compute_loo_errors_gp :274-276)."""
+    d = X.shape[1]
+    gp_e = gp_factory(X, nes, kernel)
+    priors = MapPriors(X)
+    if seed is not None:
+        np.random.seed(seed + 7919 * comm.rank)
+    starts = [priors.sample() for _ in range(n_tries)]
+    mstats: dict = {}
+    results = run_map_restarts(gp_e, priors, starts, loo_error_raw_bounds(bounds), 0.0, True, stats=mstats,
+                               return_all=True)
+    done = [r for r in results if r is not None]
+    local = np.full(d + 2, np.inf)
+    if done:
+        k = int(np.argmin([r[0] for r in done]))
+        local[0], local[1:] = done[k][0], done[k][1]
+    gathered = comm.allgather(local)
+    if not np.any(np.isfinite(gathered[:, 0])):
+        raise RuntimeError("GP fitting failed")
+    theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
+    gp_e.fit(theta[:d], float(np.exp(theta[d])), 0.0, True)
+    stats["map_batches"] = stats.get("map_batches", 0) + mstats.get("batches", 0)
+    stats["map_evals"] = stats.get("map_evals", 0) + mstats.get("evals", 0)
+    stats["map_gpu_s"] = stats.get("map_gpu_s", 0.0) + mstats.get("gpu_s", 0.0)
+    return gp_e, theta
+
+
+def global_argmax(cand, comm, candidate_offset: int, scale: float = 1.0):
+    """(value * scale, global index, point) of the best candidate over all ranks."""
+    i, v = cand.argmax()
+    if comm.size == 1:
+        return v * scale, i + candidate_offset, np.array(cand.Xc[i], dtype=float)
+    msg = np.concatenate([[v * scale, float(i + candidate_offset)], cand.Xc[i]])
+    allm = comm.allgather(msg)
+    w = pick_global_best(allm[:, 0], allm[:, 1])
+    return float(allm[w, 0]), int(allm[w, 1]), allm[w, 2:].copy()
+
+
+def find_cross_level_duplicate(Xs: dict) -> Optional[tuple]:
+    """A training input shared by two levels, as _find_input_repetition_across_levels
+    (designers.py:925-955) reports -- by a sort instead of a product over all levels' inputs."""
+    levels = sorted(Xs)
+    X = np.vstack([Xs[lv] for lv in levels])
+    tag = np.concatenate([np.full(Xs[lv].shape[0], lv) for lv in levels])
+    order = np.argsort(X[:, 0], kind="stable")
+    x0 = X[order, 0]
+    hi = np.searchsorted(x0, x0 + 2.1e-9 * np.maximum(1.0, np.abs(x0)), side="right")
+    for i in range(X.shape[0]):
+        if hi[i] <= i + 1:
+            continue
+        a = X[order[i]]
+        nb = order[i + 1 : hi[i]]
+        hit = np.nonzero(_rows_equal(X[nb], a) & (tag[nb] != tag[order[i]]))[0]
+        if hit.size:
+            return a, int(tag[order[i]]), int(tag[nb[hit[0]]])
+    return None
+
+
+# ---------------------------------------------------------------------------------------
 # the design batch
 # ---------------------------------------------------------------------------------------
 def design_batch(
@@ -176,27 +238,8 @@ def design_batch(
 
     t1 = time.perf_counter()
     # 2. errors GP: MAP estimate, restarts sharded over ranks
-    gp_e = gp_factory(X, nes, kernel)
-    priors = MapPriors(X)
-    if seed is not None:
-        np.random.seed(seed + 7919 * comm.rank)
-    starts = [priors.sample() for _ in range(n_tries)]
-    mstats: dict = {}
-    results = run_map_restarts(gp_e, priors, starts, loo_error_raw_bounds(bounds), 0.0, True, stats=mstats,
-                               return_all=True)
-    done = [r for r in results if r is not None]
-    local = np.full(d + 2, np.inf)
-    if done:
-        k = int(np.argmin([r[0] for r in done]))
-        local[0], local[1:] = done[k][0], done[k][1]
-    gathered = comm.allgather(local)
-    if not np.any(np.isfinite(gathered[:, 0])):
-        raise RuntimeError("GP fitting failed")
-    theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
-    gp_e.fit(theta[:d], float(np.exp(theta[d])), 0.0, True)
+    gp_e, theta = fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats)
     t2 = time.perf_counter()
-    stats.update(map_batches=mstats.get("batches", 0), map_evals=mstats.get("evals", 0),
-                 map_gpu_s=mstats.get("gpu_s", 0.0))
 
     # 3. PEI over this rank's candidates, batch_size rounds of arg max + repulsion update
     cand = candidates if hasattr(candidates, "pei_eval") else cand_factory(candidates)
@@ -212,12 +255,102 @@ def design_batch(
         gidx[:], vals[:] = li + candidate_offset, lv
     else:
         for s in range(batch_size):
-            i, v = cand.argmax()
-            msg = np.concatenate([[v, float(i + candidate_offset)], cand.Xc[i]])
-            allm = comm.allgather(msg)
-            w = pick_global_best(allm[:, 0], allm[:, 1])
-            vals[s], gidx[s], pts[s] = allm[w, 0], int(allm[w, 1]), allm[w, 2:]
+            vals[s], gidx[s], pts[s] = global_argmax(cand, comm, candidate_offset)
             cand.add_point(gp_e, pts[s])
     t3 = time.perf_counter()
     stats.update(loo_s=t1 - t0, map_s=t2 - t1, pei_s=t3 - t2)
     return pts, gidx, vals, theta
+
+
+def multi_level_loo_errors(levels: dict, coefficients: dict, gp_factory=DeviceGP):
+    """NES errors of the multi-level leave-one-out predictions against 0, per level
+    (compute_multi_level_loo_error_data, designers.py:1045-1105): for the left-out input x_i of
+    level l, estimate c_l (mu_-i - y_i) + sum_{j != l} c_j k_j(x_i)^T inv(cov_j C_j) y_j
+    (compute_loo_prediction :958-998, compute_zero_mean_prediction :1001-1042; the inverse is
+    nugget-free) and variance sum_j c_j^2 v_j.  ``levels[l]`` holds X, y, kernel,
+    corr_length_scales, process_var, nugget.  Returns ({level: nes}, {level: fitted GP})."""
+    dup = find_cross_level_duplicate({lv: np.asarray(v["X"], dtype=float) for lv, v in levels.items()})
+    if dup is not None:
+        raise ValueError(
+            f"Training inputs across all levels must be distinct, but found common input {dup[0]} "
+            f"at levels {dup[1]}, {dup[2]}."
+        )
+    gps, gps0 = {}, {}
+    for lv, v in levels.items():
+        X = np.ascontiguousarray(v["X"], dtype=float)
+        y = np.ascontiguousarray(v["y"], dtype=float)
+        if X.shape[0] < 2:
+            raise ValueError(
+                f"Could not perform leave-one-out calculation: levels {lv} not trained on at least two training data."
+            )
+        raw = -2.0 * np.log(np.asarray(v["corr_length_scales"], dtype=float))
+        gps[lv] = gp_factory(X, y, v["kernel"])
+        gps[lv].fit(raw, float(v["process_var"]), float(v["nugget"]))
+        if float(v["nugget"]) == 0.0:
+            gps0[lv] = gps[lv]
+        else:                                            # kinv excludes the nugget (modelling.py:1095-1113)
+            gps0[lv] = gp_factory(X, y, v["kernel"])
+            gps0[lv].fit(raw, float(v["process_var"]), 0.0)
+    out = {}
+    for lv, v in levels.items():
+        X = np.ascontiguousarray(v["X"], dtype=float)
+        y = np.ascontiguousarray(v["y"], dtype=float)
+        m, var, _ = gps[lv].loo()
+        mean = coefficients[lv] * (m - y)
+        variance = coefficients[lv] ** 2 * var
+        for other in levels:
+            if other == lv:
+                continue
+            zm, zv = gps0[other].predict(X)
+            ov = zv if gps0[other] is gps[other] else gps[other].predict(X)[1]
+            mean = mean + coefficients[other] * zm
+            variance = variance + coefficients[other] ** 2 * ov
+        sq = mean**2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            nes = (variance + sq) / np.sqrt(2.0 * variance**2 + 4.0 * variance * sq)
+        out[lv] = nes
+    return out, gps
+
+
+def multi_level_design_batch(
+    levels: dict,
+    coefficients: dict,
+    costs: dict,
+    bounds: Sequence[Sequence[float]],
+    candidates,
+    batch_size: int = 1,
+    n_tries: int = 15,
+    seed: Optional[int] = None,
+    comm=None,
+    candidate_offset: int = 0,
+    gp_factory=DeviceGP,
+    cand_factory=DeviceCandidates,
+    stats: Optional[dict] = None,
+):
+    """compute_multi_level_loo_samples (designers.py:1184-1378) over a fixed candidate set:
+    per-level errors GPs fitted to the multi-level LOO errors, then ``batch_size`` rounds of
+    [arg max over candidates of PEI_l / cost_l for every level, take the best level, add the
+    point to THAT level's repulsion set].  Returns a list of (level, global index, point, value)."""
+    comm = comm or SingleComm()
+    stats = stats if stats is not None else {}
+    nes, _ = multi_level_loo_errors(levels, coefficients, gp_factory)
+    Xc = candidates.Xc if hasattr(candidates, "Xc") else np.ascontiguousarray(candidates, dtype=float)
+    gp_e, cands = {}, {}
+    for lv in sorted(levels):
+        X = np.ascontiguousarray(levels[lv]["X"], dtype=float)
+        if not np.all(np.isfinite(nes[lv])):
+            raise FloatingPointError(f"non-finite NES error at level {lv}")
+        lvl_seed = None if seed is None else seed + 104729 * lv
+        gp_e[lv], _ = fit_errors_gp(X, nes[lv], levels[lv]["kernel"], bounds, n_tries, lvl_seed, comm, gp_factory, stats)
+        cands[lv] = cand_factory(Xc)
+        cands[lv].pei_eval(gp_e[lv], pseudopoints(X, bounds), float(np.max(nes[lv])))
+    chosen = []
+    for _ in range(batch_size):
+        best = None
+        for lv in sorted(levels):                       # max(...) keeps the first maximal level
+            v, gi, pt = global_argmax(cands[lv], comm, candidate_offset, 1.0 / costs[lv])
+            if best is None or v > best[3]:
+                best = (lv, gi, pt, v)
+        chosen.append(best)
+        cands[best[0]].add_point(gp_e[best[0]], best[2])
+    return chosen

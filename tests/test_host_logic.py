@@ -147,3 +147,60 @@ def test_design_batch_single_rank_on_oracle_device():
     oi, ov, _ = orc.pei_batch_argmax(ge, "Matern52", Xc, pseudopoints(X, bounds), float(nes.max()), 3)
     assert gidx.tolist() == oi.tolist() and np.allclose(vals, ov, rtol=1e-10)
     assert stats["map_evals"] > 0
+
+
+@needs_exauq
+def test_multi_level_loo_errors_match_reference_on_oracle_device():
+    """design.multi_level_loo_errors vs the reference's compute_multi_level_loo_error_data
+    (exauq/core/designers.py:1045-1105) run with MogpEmulator on the restated mogp."""
+    from exauq.core.designers import compute_multi_level_loo_error_data
+    from exauq.core.emulators import MogpEmulator, MogpHyperparameters
+    from exauq.core.modelling import Input, MultiLevel, MultiLevelGaussianProcess, TrainingDatum
+
+    from exauq_toolbox_b200.design import find_cross_level_duplicate, multi_level_loo_errors
+
+    rng = np.random.default_rng(4)
+    d = 2
+    Xs = {1: rng.uniform(0, 1, (14, d)), 2: rng.uniform(0, 1, (9, d)), 3: rng.uniform(0, 1, (6, d))}
+    fs = {1: lambda x: x[1] + x[0] ** 2, 2: lambda x: np.sin(3 * x[0]) * x[1], 3: lambda x: 0.1 * np.cos(5 * x[0] + x[1])}
+    hps = {1: ([0.6, 0.9], 2.0, 0.0), 2: ([0.3, 0.4], 1.5, 1e-8), 3: ([0.5, 0.5], 0.2, 0.0)}
+    data = MultiLevel({lv: [TrainingDatum(Input(*x), float(fs[lv](x))) for x in Xs[lv]] for lv in Xs})
+    ref = MultiLevelGaussianProcess([MogpEmulator(kernel="Matern52") for _ in range(3)], coefficients=[1.0, 0.8, 1.3])
+    ref.fit(data, hyperparameters=MultiLevel({k: MogpHyperparameters(*v) for k, v in hps.items()}))
+    ref_err = compute_multi_level_loo_error_data(ref)
+    levels = {lv: dict(X=Xs[lv], y=np.array([fs[lv](x) for x in Xs[lv]]), kernel="Matern52",
+                       corr_length_scales=hps[lv][0], process_var=hps[lv][1], nugget=hps[lv][2]) for lv in Xs}
+    got, _ = multi_level_loo_errors(levels, {lv: ref.coefficients[lv] for lv in Xs}, gp_factory=OracleGP)
+    for lv in Xs:
+        assert np.allclose(got[lv], [dt.output for dt in ref_err[lv]], rtol=1e-7)
+    assert find_cross_level_duplicate(Xs) is None
+    Xs[3][2] = Xs[1][5] + 3e-10
+    rep = find_cross_level_duplicate(Xs)
+    assert rep is not None and {rep[1], rep[2]} == {1, 3}
+
+
+def test_multi_level_design_batch_on_oracle_device():
+    """The level/point chosen each round maximises PEI_l / cost_l over levels and candidates, and
+    only the chosen level's repulsion set grows (exauq/core/designers.py:1357-1376)."""
+    pytest.importorskip("exauq")
+    from oracle import gp_oracle as orc
+
+    from exauq_toolbox_b200.design import multi_level_design_batch, multi_level_loo_errors, pseudopoints
+
+    rng = np.random.default_rng(7)
+    d = 2
+    bounds = [(0.0, 1.0)] * d
+    levels = {}
+    for lv, n, f in [(1, 16, lambda X: X[:, 1] + X[:, 0] ** 2), (2, 10, lambda X: np.sin(6 * X[:, 0]) * X[:, 1])]:
+        X = rng.uniform(0, 1, (n, d))
+        levels[lv] = dict(X=X, y=f(X), kernel="Matern52", corr_length_scales=[0.4, 0.5], process_var=1.2, nugget=0.0)
+    coeff, costs = {1: 1.0, 2: 1.0}, {1: 1.0, 2: 11.0}
+    Xc = orc.synthetic_candidates(300, d)
+    chosen = multi_level_design_batch(levels, coeff, costs, bounds, Xc, batch_size=4, n_tries=3, seed=11,
+                                      gp_factory=OracleGP, cand_factory=OracleCandidates)
+    assert len(chosen) == 4 and all(c[0] in (1, 2) for c in chosen)
+    assert len({(c[0], c[1]) for c in chosen}) == 4          # a (level, candidate) pair is never chosen twice
+    for lv, gi, pt, v in chosen:
+        assert np.allclose(pt, Xc[gi]) and v >= 0
+    vals = [c[3] for c in chosen]
+    assert vals[0] == max(vals)                                # the first round sees the largest PEI / cost
