@@ -241,6 +241,7 @@ def run_b200(a):
     stats = {}
 
     def step(resident_cand=None):
+        stats.clear()
         cand = resident_cand if resident_cand is not None else Xc
         return design_batch(X, y, "Matern52", ell, cov, nug, bounds, cand, batch_size=a.batch_size,
                             n_tries=a.restarts, seed=12345, comm=comm, candidate_offset=offset, stats=stats)

