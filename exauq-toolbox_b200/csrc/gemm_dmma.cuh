@@ -148,9 +148,28 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) g
         cp_async_commit();
     }
 
+    // Fragments are double-buffered in registers across k-groups AND across k-tiles: the wait +
+    // barrier for the next stage sits before the LAST k-group of the current tile, whose 32 DMMAs
+    // then cover the barrier and the first fragment loads of the next tile.
+    auto load_frags = [&](const double* a_s, const double* b_s, int kk, double (&af)[MF], double (&bf)[NF]) {
+#pragma unroll
+        for (int mf = 0; mf < MF; mf++) {
+            int m = wm * (MF * 8) + mf * 8 + g, k = kk * 4 + t;
+            af[mf] = (AL == LAYOUT_K) ? a_s[m * GEMM_LDS_K + k] : a_s[k * Cfg::LDS_A_MN + m];
+        }
+#pragma unroll
+        for (int nf = 0; nf < NF; nf++) {
+            int n = wn * (NF * 8) + nf * 8 + g, k = kk * 4 + t;
+            bf[nf] = (BL == LAYOUT_K) ? b_s[n * GEMM_LDS_K + k] : b_s[k * Cfg::LDS_B_MN + n];
+        }
+    };
+    constexpr int NKK = GEMM_BK / 4;
+    double af[2][MF], bf[2][NF];
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (nkt > 0) load_frags(sA, sB, 0, af[0], bf[0]);
+
     for (int kt = 0; kt < nkt; kt++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
         const int nk = kt + STAGES - 1;
         const bool do_load = nk < nkt;
         double* a_n = sA + (nk % STAGES) * Cfg::A_ELEMS;
@@ -158,28 +177,37 @@ __global__ void __launch_bounds__(GemmCfg<BM>::THREADS, GemmCfg<BM>::MIN_CTAS) g
         const int k_n = (kt_lo + nk) * GEMM_BK;
         const double* a_s = sA + (kt % STAGES) * Cfg::A_ELEMS;
         const double* b_s = sB + (kt % STAGES) * Cfg::B_ELEMS;
+        const double* a_x = sA + ((kt + 1) % STAGES) * Cfg::A_ELEMS;
+        const double* b_x = sB + ((kt + 1) % STAGES) * Cfg::B_ELEMS;
 #pragma unroll
-        for (int kk = 0; kk < GEMM_BK / 4; kk++) {
-            double af[MF], bf[NF];
-#pragma unroll
-            for (int mf = 0; mf < MF; mf++) {
-                int m = wm * (MF * 8) + mf * 8 + g, k = kk * 4 + t;
-                af[mf] = (AL == LAYOUT_K) ? a_s[m * GEMM_LDS_K + k] : a_s[k * Cfg::LDS_A_MN + m];
+        for (int kk = 0; kk < NKK; kk++) {
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk == NKK - 1) {
+                // all copies of this iteration were issued in the earlier k-groups
+                cp_async_commit();
+                cp_async_wait<STAGES - 2>();
+                __syncthreads();
+                if (kt + 1 < nkt) load_frags(a_x, b_x, 0, af[nxt], bf[nxt]);
+            } else {
+                load_frags(a_s, b_s, kk + 1, af[nxt], bf[nxt]);
             }
 #pragma unroll
-            for (int nf = 0; nf < NF; nf++) {
-                int n = wn * (NF * 8) + nf * 8 + g, k = kk * 4 + t;
-                bf[nf] = (BL == LAYOUT_K) ? b_s[n * GEMM_LDS_K + k] : b_s[k * Cfg::LDS_B_MN + n];
-            }
-#pragma unroll
             for (int mf = 0; mf < MF; mf++) {
 #pragma unroll
-                for (int nf = 0; nf < NF; nf++) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
-                if (do_load && mf == MF / 4) gemm_load_tile_part<AL, BM, THREADS>(a_n, A, p.lda, m0, k_n, tid, kk);
-                if (do_load && mf == (3 * MF) / 4) gemm_load_tile_part<BL, GEMM_BN, THREADS>(b_n, B, p.ldb, n0, k_n, tid, kk);
+                for (int nf = 0; nf < NF; nf++) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[cur][mf], bf[cur][nf]);
+                if (do_load && kk < NKK - 1) {
+                    // 4 parts of each operand over the first 3 k-groups: A parts {0,1 | 2 | 3}, same for B
+                    if (mf == MF / 4) {
+                        gemm_load_tile_part<AL, BM, THREADS>(a_n, A, p.lda, m0, k_n, tid, kk == 0 ? 0 : kk + 1);
+                        if (kk == 0) gemm_load_tile_part<AL, BM, THREADS>(a_n, A, p.lda, m0, k_n, tid, 1);
+                    }
+                    if (mf == (3 * MF) / 4) {
+                        gemm_load_tile_part<BL, GEMM_BN, THREADS>(b_n, B, p.ldb, n0, k_n, tid, kk == 0 ? 0 : kk + 1);
+                        if (kk == 0) gemm_load_tile_part<BL, GEMM_BN, THREADS>(b_n, B, p.ldb, n0, k_n, tid, 1);
+                    }
+                }
             }
         }
-        cp_async_commit();
     }
     cp_async_wait<0>();
 
