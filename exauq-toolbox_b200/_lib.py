@@ -41,12 +41,14 @@ SIGNATURES = {
     "exq_gp_destroy": (C.c_int, [_vp]),
     "exq_gp_fit": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]),
     "exq_gp_predict": (C.c_int, [_vp, _dp, C.c_int64, _dp, _dp]),
+    "exq_gp_cross_cov": (C.c_int, [_vp, _dp, C.c_int64, _dp]),
     "exq_gp_loo": (C.c_int, [_vp, _dp, _dp, _dp]),
     "exq_gp_loo_refit": (C.c_int, [_vp, _ip, C.c_int, _dp, _dp, _dp]),
     "exq_gp_kinv": (C.c_int, [_vp, _dp]),
     "exq_gp_logpost_batch": (C.c_int, [_vp, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _ip, _dp]),
     "exq_cand_create": (C.c_int, [C.c_int64, C.c_int, _dp, C.POINTER(_vp)]),
     "exq_cand_destroy": (C.c_int, [_vp]),
+    "exq_cand_set_points": (C.c_int, [_vp, _dp]),
     "exq_pei_eval": (C.c_int, [_vp, _vp, _dp, C.c_int, C.c_double]),
     "exq_pei_argmax": (C.c_int, [_vp, _lp, _dp]),
     "exq_pei_add_point": (C.c_int, [_vp, _vp, _dp]),
@@ -194,6 +196,12 @@ class DeviceGP:
         check(load().exq_gp_predict(self._h, _d(Xc), Xc.shape[0], _d(mean), _d(var)), "exq_gp_predict")
         return mean, var
 
+    def cross_cov(self, Xq) -> np.ndarray:
+        Xq = as_f64(Xq).reshape(-1, self.d)
+        out = np.empty((Xq.shape[0], self.N))
+        check(load().exq_gp_cross_cov(self._h, _d(Xq), Xq.shape[0], _d(out)), "exq_gp_cross_cov")
+        return out
+
     def loo(self):
         mean, var, nes = np.empty(self.N), np.empty(self.N), np.empty(self.N)
         check(load().exq_gp_loo(self._h, _d(mean), _d(var), _d(nes)), "exq_gp_loo")
@@ -248,6 +256,11 @@ class DeviceCandidates:
             self.close()
         except Exception:
             pass
+
+    def set_points(self, Xc):
+        Xc = as_f64(Xc).reshape(self.M, self.d)
+        check(load().exq_cand_set_points(self._h, _d(Xc)), "exq_cand_set_points")
+        self.Xc = Xc
 
     def pei_eval(self, gp: DeviceGP, rep, tmax: float):
         rep = as_f64(rep).reshape(-1, self.d) if rep is not None and len(rep) else np.empty((0, self.d))

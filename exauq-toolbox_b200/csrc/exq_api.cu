@@ -710,6 +710,35 @@ int exq_gp_predict(exq_gp_t gp, const double* Xc, int64_t M, double* mean, doubl
     return rc;
 }
 
+int exq_gp_cross_cov(exq_gp_t gp, const double* Xq, int64_t n, double* out) {
+    REQUIRE_READY();
+    if (!gp || !Xq || !out || n < 1) return fail(EXQ_ERR_ARG, "exq_gp_cross_cov: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_cross_cov: GP has not been fitted");
+    const int d = gp->d, Np = gp->Np;
+    const int64_t npad = ((n + 127) / 128) * 128;
+    int rc = ensure_pred_scratch(gp, std::max<int64_t>(npad, 128));
+    if (rc) return rc;
+    double* xq = nullptr;
+    CUDA_TRY(cudaMalloc(&xq, (size_t)npad * d * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(xq, 0, (size_t)npad * d * sizeof(double), g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xq, Xq, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) {
+        AsmArgs a{};
+        a.Xi = xq; a.Xj = gp->X; a.theta = gp->fit.theta; a.out = gp->KcT;
+        a.ld = Np; a.n_i = (int)n; a.n_j = (int)gp->N; a.d = d; a.kernel_id = gp->kernel_id;
+        a.sym = 0; a.scale_sigma2 = 1;
+        rc = launch_assemble(a, (int)npad, Np, 1);
+    }
+    if (e == cudaSuccess && !rc)
+        e = cudaMemcpy2DAsync(out, (size_t)gp->N * sizeof(double), gp->KcT, (size_t)Np * sizeof(double),
+                              (size_t)gp->N * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(xq);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string("exq_gp_cross_cov: ") + cudaGetErrorString(e));
+    return EXQ_OK;
+}
+
 int exq_gp_loo(exq_gp_t gp, double* mean, double* var, double* nes) {
     REQUIRE_READY();
     if (!gp) return fail(EXQ_ERR_ARG, "exq_gp_loo: bad argument");
@@ -977,6 +1006,15 @@ int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out) {
         return fail(EXQ_ERR_CUDA, std::string("exq_cand_create: ") + cudaGetErrorString(e));
     }
     *out = c;
+    return EXQ_OK;
+}
+
+int exq_cand_set_points(exq_cand_t c, const double* Xc) {
+    REQUIRE_READY();
+    if (!c || !Xc) return fail(EXQ_ERR_ARG, "exq_cand_set_points: bad argument");
+    CUDA_TRY(cudaMemcpyAsync(c->Xc, Xc, (size_t)c->M * c->d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    c->evaluated = false;
     return EXQ_OK;
 }
 

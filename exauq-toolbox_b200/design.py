@@ -262,6 +262,41 @@ def design_batch(
     return pts, gidx, vals, theta
 
 
+def maximise_pei_de(gp_e, bounds: Sequence[Sequence[float]], repulsion_points, max_target: float,
+                    seed: Optional[int] = None, cand_factory=DeviceCandidates, popsize: int = 15, **de_kwargs):
+    """Continuous maximisation of the pseudo-expected improvement of a fitted errors GP over the
+    domain box, with the optimiser the reference uses -- scipy ``differential_evolution`` with
+    ``tol = atol = 1e-9`` (exauq/utilities/optimisation.py:14-104) -- but with every generation's
+    population evaluated in ONE device call (``vectorized=True``, ``updating='deferred'``; the
+    reference's default immediate updating is inherently one point at a time).  Returns
+    ``(x, pei(x))`` like ``maximise``.  SURVEY.md section 8f item 1."""
+    import scipy.optimize
+
+    d = len(bounds)
+    rep = np.asarray(repulsion_points, dtype=float).reshape(-1, d) if len(repulsion_points) else None
+    state = {"cand": None}
+
+    def neg_pei(x):
+        pts = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=float).T))     # (S, d)
+        if pts.shape[1] != d:
+            pts = pts.reshape(-1, d)
+        c = state["cand"]
+        if c is None or c.M != pts.shape[0]:
+            c = state["cand"] = cand_factory(pts)
+        else:
+            c.set_points(pts)
+        c.pei_eval(gp_e, rep, max_target)
+        vals = -c.download("pei")
+        return vals if np.ndim(x) > 1 else float(vals[0])
+
+    result = scipy.optimize.differential_evolution(neg_pei, bounds=[tuple(b) for b in bounds], tol=1e-9, atol=1e-9,
+                                                   seed=seed, vectorized=True, updating="deferred", popsize=popsize,
+                                                   **de_kwargs)
+    if not result.success:
+        raise RuntimeError(f"Maximisation failed to converge: {result.message}")
+    return np.array(result.x, dtype=float), -float(result.fun)
+
+
 def multi_level_loo_errors(levels: dict, coefficients: dict, gp_factory=DeviceGP):
     """NES errors of the multi-level leave-one-out predictions against 0, per level
     (compute_multi_level_loo_error_data, designers.py:1045-1105): for the left-out input x_i of

@@ -480,9 +480,16 @@ class B200GaussianProcess(AbstractGaussianProcess):
         return _lib.corr(self._kernel_name, corr_raw, inputs_to_array(inputs1), inputs_to_array(inputs2))
 
     def covariance_matrix(self, inputs: Sequence[Input]) -> np.ndarray:
-        """As ``MogpEmulator.covariance_matrix`` (exauq/core/emulators.py:569-610)."""
+        """As ``MogpEmulator.covariance_matrix`` (exauq/core/emulators.py:569-610):
+        ``process_var * correlation(inputs, training_inputs)`` with the same checks, computed
+        against the training inputs already resident on the device (``exq_gp_cross_cov``)."""
+        if not self.training_data:
+            return np.array([])
         try:
-            return super().covariance_matrix(inputs)
+            if len(inputs) == 0:
+                return np.array([])
+            if not all(isinstance(x, Input) for x in inputs):
+                raise TypeError
         except TypeError:
             if not isinstance(inputs, Sequence):
                 raise TypeError(
@@ -494,6 +501,7 @@ class B200GaussianProcess(AbstractGaussianProcess):
                     "Expected all elements of 'inputs' to be of type Input objects, "
                     "but one or more elements were of an unexpected type."
                 ) from None
+        return self._real_state().dev.cross_cov(inputs_to_array(inputs, self._input_dim()))
 
     # ------------------------------------------------------------------ batched extras
     def logpost_batch(self, theta_raw, with_prior: bool = True):

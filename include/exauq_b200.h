@@ -96,6 +96,12 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
  * exauq/core/emulators.py:612-667 (line 649), for a whole batch of inputs. */
 int exq_gp_predict(exq_gp_t gp, const double* Xc, int64_t M, double* mean, double* var);
 
+/* Covariance of n query points with the training inputs: out[n][N] = cov * C(Xq, train) (no
+ * nugget), using the resident training data and the fitted hyperparameters.
+ * Replaces AbstractGaussianProcess.covariance_matrix, exauq/core/modelling.py:1042-1080
+ * (MogpEmulator.covariance_matrix, exauq/core/emulators.py:569-610). */
+int exq_gp_cross_cov(exq_gp_t gp, const double* Xq, int64_t n, double* out);
+
 /* Leave-one-out sweep with the fitted hyperparameters: for every i, the prediction at x_i
  * of the GP refitted on data \ {i}, and its NES error against y_i.
  * Replaces the loop compute_loo_errors_gp runs, exauq/core/designers.py:263-272
@@ -126,6 +132,8 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
 /* ---- candidate sets resident in HBM (PEI maximisation over fixed candidates) -------- */
 int exq_cand_create(int64_t M, int d, const double* Xc, exq_cand_t* out);
 int exq_cand_destroy(exq_cand_t c);
+/* overwrite the coordinates of an existing set (same M, d): one H2D copy, no reallocation */
+int exq_cand_set_points(exq_cand_t c, const double* Xc);
 
 /* Evaluate mean, variance and pseudo-expected improvement of the fitted GP at every
  * candidate.  rep[n_rep][d] are the repulsion points other than the training inputs

@@ -50,6 +50,9 @@ class OracleCandidates:
         self.M, self.d = self.Xc.shape
         self.pei = None
 
+    def set_points(self, Xc):
+        self.Xc = np.asarray(Xc, float).reshape(self.M, self.d)
+
     def pei_eval(self, gp, rep, tmax):
         self.pei = orc.pei(gp.gp, gp.kernel, self.Xc, rep, tmax)
 

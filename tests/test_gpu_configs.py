@@ -128,3 +128,23 @@ def test_config4_mle_restarts_d20(exq, orc):
     assert np.all(info == 0)
     fd = (val[1] - val[2]) / (2 * eps)
     assert abs(fd - grad[0] @ direction) <= 1e-5 * max(1.0, abs(fd))
+
+
+def test_vectorised_de_maximiser_on_device(exq, orc):
+    """Continuous PEI maximisation with the population evaluated on the GPU finds
+    the same maximum as the same optimiser driven by the oracle."""
+    pytest.importorskip("exauq")
+    from fakes import OracleCandidates, OracleGP
+
+    from exauq_toolbox_b200.design import maximise_pei_de, pseudopoints
+
+    X, y = orc.synthetic_problem(200, 3)
+    bounds = [(0.0, 1.0)] * 3
+    raw = np.full(3, -2 * np.log(0.3))
+    dev = exq.DeviceGP(X, y, "Matern52").fit(raw, 1.1, 0.0)
+    ref = OracleGP(X, y, "Matern52").fit(raw, 1.1, 0.0)
+    rep = pseudopoints(X, bounds)
+    x, v = maximise_pei_de(dev, bounds, rep, float(y.max()), seed=5)
+    xo, vo = maximise_pei_de(ref, bounds, rep, float(y.max()), seed=5, cand_factory=OracleCandidates)
+    assert abs(v - vo) <= 1e-6 * abs(vo) and np.allclose(x, xo, atol=1e-5)
+    assert np.all(x >= 0) and np.all(x <= 1)

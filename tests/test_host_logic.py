@@ -204,3 +204,28 @@ def test_multi_level_design_batch_on_oracle_device():
         assert np.allclose(pt, Xc[gi]) and v >= 0
     vals = [c[3] for c in chosen]
     assert vals[0] == max(vals)                                # the first round sees the largest PEI / cost
+
+
+@needs_exauq
+def test_vectorised_de_maximiser_finds_the_reference_maximum():
+    """design.maximise_pei_de (population evaluated per generation, oracle device) vs the
+    reference's maximise(pei.compute) (exauq/utilities/optimisation.py:14-104) on the same PEI."""
+    from exauq.core.designers import PEICalculator
+    from exauq.core.emulators import MogpEmulator, MogpHyperparameters
+    from exauq.core.modelling import Input, SimulatorDomain, TrainingDatum
+    from exauq.utilities.optimisation import maximise
+
+    from exauq_toolbox_b200.design import maximise_pei_de, pseudopoints
+
+    g = load_golden("fixed_matern_d3_n40.json")
+    X, y = np.array(g["X"])[:, :2], np.array(g["y"])
+    bounds = [(0.0, 1.0)] * 2
+    hp = ([0.4, 0.4], 1.3, 0.0)
+    ref = MogpEmulator(kernel="Matern52")
+    ref.fit([TrainingDatum(Input(*x), float(t)) for x, t in zip(X, y)], hyperparameters=MogpHyperparameters(*hp))
+    pei = PEICalculator(SimulatorDomain(bounds), ref)
+    x_ref, v_ref = maximise(lambda x: pei.compute(x), SimulatorDomain(bounds), seed=3)
+    dev = OracleGP(X, y, "Matern52").fit(-2 * np.log(np.array(hp[0])), hp[1], hp[2])
+    x, v = maximise_pei_de(dev, bounds, pseudopoints(X, bounds), float(y.max()), seed=3, cand_factory=OracleCandidates)
+    assert abs(v - v_ref) <= 1e-6 * abs(v_ref)
+    assert np.allclose(x, np.array(x_ref), atol=1e-4)
