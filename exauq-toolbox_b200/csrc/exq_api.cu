@@ -231,6 +231,7 @@ struct exq_gp_s {
     Sys batch;                              // MLE restarts / LOO refits
     // prediction scratch
     double *KcT = nullptr, *P = nullptr;   // views of the global scratch
+    double* zsmall = nullptr;              // [8][Np] for the small-M variance path
     int64_t chunk = 0;
     double* rep = nullptr;
     int rep_cap = 0;
@@ -409,14 +410,29 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
         a.ld = Np; a.n_i = (int)mc; a.n_j = (int)gp->N; a.d = gp->d; a.kernel_id = gp->kernel_id;
         a.sym = 0; a.scale_sigma2 = 1;
         if ((rc = launch_assemble(a, (int)mc_pad, Np, 1))) return rc;
+        if (mc <= 8) {
+            // a handful of points (scalar predict calls from the unchanged designers): z = Linv k by
+            // one triangular mat-vec per point instead of a one-column-tile GEMM
+            if (!gp->zsmall) CUDA_TRY(cudaMalloc(&gp->zsmall, (size_t)8 * Np * sizeof(double)));
+            ProfMark m0 = prof_begin(EXQ_PROF_STREAM, (double)mc * Np * Np, (double)mc * Np * Np * 4.0);
+            trmv_lower_kernel<<<dim3(Np / 8, 1, (unsigned)mc), 256, 0, g.stream>>>(gp->fit.Linv, Np, 0, gp->KcT, Np, gp->zsmall,
+                                                                               Np, Np);
+            prof_end(m0);
+            LAUNCH_CHECK("trmv_lower_kernel");
+            m0 = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+            sumsq_rows_kernel<<<(unsigned)mc, 256, 0, g.stream>>>(gp->zsmall, Np, Np, gp->P);
+            prof_end(m0);
+            LAUNCH_CHECK("sumsq_rows_kernel");
+        } else {
         GemmArgs ga{};
         ga.A = gp->fit.Linv; ga.B = gp->KcT; ga.C = gp->P;
         ga.lda = Np; ga.ldb = Np; ga.ldc = mc_pad;
         ga.M = Np; ga.N = (int)mc_pad; ga.K = Np;
         ga.krange = KR_LE_I; ga.lower_only = 0; ga.cmode = C_COLSUMSQ; ga.raster = 8;
         if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
+        }
         FinArgs f{};
-        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = Np / 128;
+        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : Np / 128;
         f.alpha = gp->fit.alpha; f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep;
         f.N = (int)gp->N; f.Np = Np; f.d = gp->d; f.kernel_id = gp->kernel_id; f.m_valid = (int)mc;
         f.tmax = tmax; f.want_pei = want_pei;
@@ -649,7 +665,7 @@ int exq_gp_create(int64_t N, int d, const double* X, const double* y, int kernel
 int exq_gp_destroy(exq_gp_t gp) {
     if (!gp) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
-    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep);
+    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep); cudaFree(gp->zsmall);
     sys_release(gp->fit);
     sys_release(gp->batch);
     delete gp;

@@ -325,6 +325,22 @@ __global__ void __launch_bounds__(256) predict_finalize_kernel(FinArgs p) {
     }
 }
 
+// sum of squares of each of the M vectors z[c][0..n) -> out[c]  (small-M variance path)
+__global__ void __launch_bounds__(256) sumsq_rows_kernel(const double* __restrict__ z, int64_t ld, int n,
+                                                         double* __restrict__ out) {
+    __shared__ double red[8];
+    const double* row = z + (int64_t)blockIdx.x * ld;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += 256) s = fma(row[j], row[j], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) s += red[k];
+        out[blockIdx.x] = s;
+    }
+}
+
 // ---- argmax over M values, lowest index wins ties, NaN ignored ------------------------
 struct ArgPair { double v; long long i; };
 __device__ __forceinline__ bool arg_better(double v, long long i, double bv, long long bi) {
