@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("EXQ_LIB", os.path.join(_HERE, "libexauq_b200.so"))  #
 
 EXQ_OK, EXQ_ERR_ARG, EXQ_ERR_CUDA, EXQ_ERR_STATE, EXQ_NOT_PD = 0, -1, -2, -3, 1
 KERNEL_IDS = {"Matern52": 0, "SquaredExponential": 1, "ProductMat52": 2}
-NUGGET_FIXED, NUGGET_ADAPTIVE = 0, 1
+NUGGET_FIXED, NUGGET_ADAPTIVE, NUGGET_FIT = 0, 1, 2
 PROF_GEMM_PREDICT, PROF_GEMM_FACTOR, PROF_LEAF, PROF_ASSEMBLE, PROF_STREAM = range(5)
 
 # every symbol include/exauq_b200.h declares: (name, restype, argtypes)
@@ -220,15 +220,18 @@ class DeviceGP:
         check(load().exq_gp_kinv(self._h, _d(out)), "exq_gp_kinv")
         return out
 
-    def logpost_batch(self, theta_raw, nugget: float = 0.0, adaptive: bool = False, want_grad: bool = True):
-        theta_raw = as_f64(theta_raw).reshape(-1, self.d + 1)
+    def logpost_batch(self, theta_raw, nugget: float = 0.0, adaptive: bool = False, want_grad: bool = True,
+                      fit_nugget: bool = False):
+        """``fit_nugget``: rows of ``theta_raw`` carry ln(nugget) as a last, (d+2)-th entry."""
+        npar = self.d + 1 + (1 if fit_nugget else 0)
+        theta_raw = as_f64(theta_raw).reshape(-1, npar)
         R = theta_raw.shape[0]
         val = np.empty(R)
-        grad = np.empty((R, self.d + 1)) if want_grad else None
+        grad = np.empty((R, npar)) if want_grad else None
         info = np.zeros(R, dtype=np.int32)
         nug = np.empty(R)
-        check(load().exq_gp_logpost_batch(self._h, R, _d(theta_raw), float(nugget),
-                                          NUGGET_ADAPTIVE if adaptive else NUGGET_FIXED, _d(val),
+        mode = NUGGET_FIT if fit_nugget else (NUGGET_ADAPTIVE if adaptive else NUGGET_FIXED)
+        check(load().exq_gp_logpost_batch(self._h, R, _d(theta_raw), float(nugget), mode, _d(val),
                                           _d(grad) if want_grad else None, info.ctypes.data_as(_ip), _d(nug)),
               "exq_gp_logpost_batch")
         return val, grad, info, nug

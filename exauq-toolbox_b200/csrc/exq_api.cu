@@ -883,6 +883,8 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
     REQUIRE_READY();
     if (!gp || R < 1 || !theta_raw || !val) return fail(EXQ_ERR_ARG, "exq_gp_logpost_batch: bad argument");
     const int N = (int)gp->N, d = gp->d, Np = gp->Np;
+    const bool fit_nug = (nugget_mode == EXQ_NUGGET_FIT);
+    const int np_raw = d + 1 + (fit_nug ? 1 : 0);     // raw parameters per restart
     int64_t per = (int64_t)3 * Np * Np * 8;
     int Bmax = (int)std::max<int64_t>(1, std::min<int64_t>(128, ((int64_t)96 << 30) / per));
     Bmax = std::min(Bmax, R);
@@ -900,7 +902,11 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
         std::vector<double> nug(B, nugget_mode == EXQ_NUGGET_ADAPTIVE ? 0.0 : nugget);
         std::vector<int> bad(B, 0);
         for (int b = 0; b < B; b++) {
-            const double* raw = theta_raw + (size_t)(b0 + b) * (d + 1);
+            const double* raw = theta_raw + (size_t)(b0 + b) * np_raw;
+            if (fit_nug) {
+                nug[b] = exp(raw[d + 1]);
+                if (!isfinite(nug[b])) bad[b] = 1, nug[b] = 0.0;
+            }
             for (int k = 0; k < d; k++) {
                 thb[(size_t)b * (d + 2) + k] = exp(raw[k]);
                 if (!isfinite(thb[(size_t)b * (d + 2) + k])) bad[b] = 1;
@@ -972,7 +978,7 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
             const bool failed = bad[b] || info[b] != 0;
             val[b0 + b] = failed ? NAN : 0.5 * (ldq[2 * b] + ldq[2 * b + 1] + N * ln2pi);
             if (grad)
-                for (int k = 0; k < d + 1; k++) grad[(size_t)(b0 + b) * (d + 1) + k] = failed ? NAN : gh[(size_t)b * (d + 2) + k];
+                for (int k = 0; k < np_raw; k++) grad[(size_t)(b0 + b) * np_raw + k] = failed ? NAN : gh[(size_t)b * (d + 2) + k];
             if (info_out) info_out[b0 + b] = failed ? EXQ_NOT_PD : 0;
             if (nugget_used) nugget_used[b0 + b] = nug[b];
         }

@@ -496,6 +496,25 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
                     r2 += gk[k];
                 } else gk[k] = 0.0;
             }
+            if (kernel_id == EXQ_KERNEL_PRODMAT52) {
+                // K = prod_k m(g_k):  dK/draw_k = K * m'(g_k)/m(g_k) * g_k  (mogp ProductMat52.kernel_deriv)
+                double cvp = 1.0;
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) {
+                    if (k < d) {
+                        double s5 = sqrt(5.0 * gk[k]), e = exp(-s5);
+                        double mk = (1.0 + s5 + (5.0 / 3.0) * gk[k]) * e;
+                        double dk = (-5.0 / 6.0) * (1.0 + s5) * e;
+                        cvp *= mk;
+                        gk[k] = gk[k] * dk / mk;      // logarithmic derivative factor
+                    }
+                }
+                const double fp = W * sigma2 * cvp;
+#pragma unroll
+                for (int k = 0; k < DMAX; k++) acc[k] = fma(fp, gk[k], acc[k]);
+                acc[DMAX] += fp;
+                continue;
+            }
             double cv, dv;
             if (kernel_id == EXQ_KERNEL_MATERN52) {
                 double s5 = sqrt(5.0 * r2), e = exp(-s5);

@@ -312,20 +312,24 @@ class B200GaussianProcess(AbstractGaussianProcess):
         """MAP estimation: multi-restart L-BFGS-B on the negative log-posterior, as
         ``fit_GP_MAP`` / ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:51-346), with
         objective and gradient evaluated on the GPU for all restarts at once."""
-        if self._nugget == "fit":
-            raise NotImplementedError("nugget='fit' estimation is not available on this backend yet")
         raw_bounds = self._compute_raw_param_bounds(bounds) if bounds is not None else None
         d = X.shape[1]
+        fit_nugget = self._nugget == "fit"
+        if fit_nugget and raw_bounds is not None:
+            raw_bounds = tuple(raw_bounds) + ((None, None),)      # the nugget itself is unbounded
         dev = DeviceGP(X, y, self._kernel_name)
-        priors = MapPriors(X)
+        priors = MapPriors(X, fit_nugget=fit_nugget)
         nugget = 0.0 if isinstance(self._nugget, str) else float(self._nugget)
-        adaptive = isinstance(self._nugget, str)
+        adaptive = self._nugget == "adaptive"
         starts = [priors.sample() for _ in range(self._n_tries)]
-        best = run_map_restarts(dev, priors, starts, raw_bounds, nugget, adaptive)
+        best = run_map_restarts(dev, priors, starts, raw_bounds, nugget, adaptive, fit_nugget=fit_nugget)
         if best is None:
             raise RuntimeError("GP fitting failed")
         theta = best
-        dev.fit(theta[:d], float(np.exp(theta[d])), nugget, adaptive)
+        if fit_nugget:
+            dev.fit(theta[:d], float(np.exp(theta[d])), float(np.exp(theta[d + 1])), False)
+        else:
+            dev.fit(theta[:d], float(np.exp(theta[d])), nugget, adaptive)
         fitted = GaussianProcessHyperparameters(
             corr_length_scales=np.exp(-0.5 * theta[:d]),
             process_var=float(np.exp(theta[d])),
@@ -539,8 +543,8 @@ class _Rendezvous:
     """Batches objective evaluations requested concurrently by the restart threads into one
     ``exq_gp_logpost_batch`` call per round (hard part 5)."""
 
-    def __init__(self, dev: DeviceGP, n_workers: int, nugget: float, adaptive: bool):
-        self.dev, self.nugget, self.adaptive = dev, nugget, adaptive
+    def __init__(self, dev: DeviceGP, n_workers: int, nugget: float, adaptive: bool, fit_nugget: bool = False):
+        self.dev, self.nugget, self.adaptive, self.fit_nugget = dev, nugget, adaptive, fit_nugget
         self.active = n_workers
         self.cv = threading.Condition()
         self.pending: dict[int, np.ndarray] = {}
@@ -555,7 +559,10 @@ class _Rendezvous:
         self.pending.clear()
         t0 = time.perf_counter()
         try:
-            val, grad, info, _ = self.dev.logpost_batch(thetas, self.nugget, self.adaptive)
+            if self.fit_nugget:
+                val, grad, info, _ = self.dev.logpost_batch(thetas, self.nugget, self.adaptive, fit_nugget=True)
+            else:
+                val, grad, info, _ = self.dev.logpost_batch(thetas, self.nugget, self.adaptive)
             for i, k in enumerate(keys):
                 self.results[k] = (val[i], grad[i], int(info[i]), None)
         except Exception as exc:  # propagate to every waiting worker
@@ -583,7 +590,7 @@ class _Rendezvous:
 
 
 def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, adaptive: bool,
-                     stats: Optional[dict] = None, return_all: bool = False):
+                     stats: Optional[dict] = None, return_all: bool = False, fit_nugget: bool = False):
     """One scipy L-BFGS-B minimisation per starting point, as the restart loop of
     ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:309-335); each optimiser runs in
     its own thread and all objective/gradient requests of a round are evaluated in one
@@ -592,7 +599,7 @@ def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, 
     negative log-posterior, or None if every restart failed (``return_all``: the list of
     ``(value, theta)`` / ``None`` per start instead)."""
     d = dev.d
-    rv = _Rendezvous(dev, len(starts), nugget, adaptive)
+    rv = _Rendezvous(dev, len(starts), nugget, adaptive, fit_nugget)
     out: list[Optional[tuple[float, np.ndarray]]] = [None] * len(starts)
 
     def worker(wid: int, theta0: np.ndarray):
@@ -602,7 +609,7 @@ def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, 
             key = np.asarray(theta, dtype=float).tobytes()
             if key not in cache:
                 cache.clear()
-                if not np.all(np.isfinite(np.exp(theta[: d + 1]))):
+                if not np.all(np.isfinite(np.exp(theta))):
                     raise FloatingPointError("overflow in hyperparameter transform")
                 val, grad, info, exc = rv.evaluate(wid, theta)
                 if exc is not None:

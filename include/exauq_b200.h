@@ -41,6 +41,7 @@ extern "C" {
 /* nugget modes: mogp GaussianProcess(nugget=...) as passed through exauq/core/emulators.py:129-141 */
 #define EXQ_NUGGET_FIXED 0    /* value supplied (float nugget, or 'fit' after estimation) */
 #define EXQ_NUGGET_ADAPTIVE 1 /* 0 unless Cholesky fails, then mean(diag K)*1e-6*10^k, k < 5 */
+#define EXQ_NUGGET_FIT 2      /* exq_gp_logpost_batch only: the nugget is the last raw parameter (ln nugget) */
 
 typedef struct exq_gp_s* exq_gp_t;
 typedef struct exq_cand_s* exq_cand_t;
@@ -121,7 +122,8 @@ int exq_gp_kinv(exq_gp_t gp, double* out);
 
 /* Negative log-likelihood and its gradient for R hyperparameter vectors at once.
  * theta_raw[R][d+1] = (corr_raw[d], ln cov); nugget handling as in exq_gp_fit (one setting
- * for all R).  val[r] = 0.5*(log|K| + y^T K^-1 y + N ln 2 pi); grad[r][d+1] = d val / d raw;
+ * for all R).  With EXQ_NUGGET_FIT the rows have d+2 entries (..., ln nugget) and so do the
+ * gradient rows.  val[r] = 0.5*(log|K| + y^T K^-1 y + N ln 2 pi); grad[r][.] = d val / d raw;
  * info[r] = 0 or EXQ_NOT_PD; nugget_used[r] as in exq_gp_fit.  Priors are added by the host.
  * Replaces mogp GaussianProcess.logposterior / logpost_deriv as driven by
  * _fit_single_GP_MAP, exauq/utilities/mogp_fitting.py:289-346 (lines 318-324). */

@@ -72,7 +72,7 @@ def neg_log_likelihood_grad(X, y, kernel: str, theta_raw, nugget=0.0):
     X = np.asarray(X, float)
     d = X.shape[1]
     gp = mogp.GaussianProcess(X, np.asarray(y, float), kernel=kernel, nugget=nugget,
-                              priors=GPPriors(n_corr=d, nugget_type="adaptive" if nugget == "adaptive" else "fixed"))
+                              priors=GPPriors(n_corr=d, nugget_type=nugget if isinstance(nugget, str) else "fixed"))
     theta_raw = np.asarray(theta_raw, float)
     val = gp.logposterior(theta_raw)
     grad = gp.logpost_deriv(theta_raw)

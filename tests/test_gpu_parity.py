@@ -127,13 +127,47 @@ def test_seeded_sizes_against_oracle(exq, orc, kernel, N, d):
         assert close(lm[idx], om) and close(lv[idx], ov) and close(ln[idx], on)
         rm, rv, rn = dev.loo_refit(idx)
         assert close(rm, om) and close(rv, ov) and close(rn, on)
-    if kernel != "ProductMat52":
+    if True:
         th = np.concatenate([corr_raw, [np.log(cov)]])[None, :] + np.random.default_rng(5).uniform(-0.3, 0.3, (3, d + 1))
         val, grad, info, _ = dev.logpost_batch(th, nug)
         for r in range(3):
             ov_, og = orc.neg_log_likelihood_grad(X, y, kernel, th[r], nug)
             assert relerr(val[r], ov_) < 1e-9
             assert np.allclose(grad[r], og, rtol=1e-7, atol=1e-8 * np.max(np.abs(og)))
+
+
+def test_fitted_nugget_logposterior_and_estimation(exq, orc):
+    """nugget='fit' (mogp: the nugget is a (d+2)-th raw parameter with an inverse-gamma prior):
+    value and gradient incl. d/d ln(nugget) vs the oracle, then a full MAP fit through the
+    drop-in class vs the reference's MogpEmulator(nugget='fit') with the same numpy seed."""
+    X, y = orc.synthetic_problem(120, 3)
+    y = y + 0.05 * np.random.default_rng(0).standard_normal(y.shape)
+    dev = exq.DeviceGP(X, y, "Matern52")
+    rng = np.random.default_rng(8)
+    th = np.concatenate([rng.uniform(-0.5, 1.5, (4, 3)), rng.uniform(-0.5, 0.5, (4, 1)), rng.uniform(-9, -3, (4, 1))], axis=1)
+    val, grad, info, nug = dev.logpost_batch(th, fit_nugget=True)
+    for r in range(4):
+        ov, og = orc.neg_log_likelihood_grad(X, y, "Matern52", th[r], "fit")
+        assert info[r] == 0 and abs(val[r] - ov) <= 1e-9 * abs(ov)
+        assert np.allclose(grad[r], og, rtol=1e-7, atol=1e-8 * np.max(np.abs(og)))
+        assert np.isclose(nug[r], np.exp(th[r, -1]))
+    pytest.importorskip("exauq")
+    from exauq.core.emulators import MogpEmulator
+    from exauq.core.modelling import Input, TrainingDatum
+
+    from exauq_toolbox_b200.gp import B200GaussianProcess
+
+    data = [TrainingDatum(Input(*x), float(t)) for x, t in zip(X, y)]
+    np.random.seed(2)
+    ref = MogpEmulator(kernel="Matern52", nugget="fit")
+    ref.fit(data)
+    np.seterr(all="warn")
+    np.random.seed(2)
+    gp = B200GaussianProcess(kernel="Matern52", nugget="fit")
+    gp.fit(data)
+    a, b = gp.fit_hyperparameters, ref.fit_hyperparameters
+    assert np.allclose(a.corr_length_scales, b.corr_length_scales, rtol=1e-4)
+    assert np.isclose(a.process_var, b.process_var, rtol=1e-4) and np.isclose(a.nugget, b.nugget, rtol=1e-3)
 
 
 def test_pei_batch_selects_same_indices(exq, orc):
