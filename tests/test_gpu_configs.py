@@ -148,3 +148,55 @@ def test_vectorised_de_maximiser_on_device(exq, orc):
     xo, vo = maximise_pei_de(ref, bounds, rep, float(y.max()), seed=5, cand_factory=OracleCandidates)
     assert abs(v - vo) <= 1e-6 * abs(vo) and np.allclose(x, xo, atol=1e-5)
     assert np.all(x >= 0) and np.all(x <= 1)
+
+
+def test_full_size_design_batch_selects_oracle_indices(exq, orc):
+    """The bench workload's size (N=4096, d=8) with a reduced candidate set: given the errors-GP
+    hyperparameters the GPU estimated, the oracle recomputes the LOO errors, the PEI of every
+    candidate and the batch arg max, and must pick the same candidates."""
+    pytest.importorskip("exauq")
+    from exauq_toolbox_b200.design import design_batch, pseudopoints
+
+    N, d, M, bs = 4096, 8, 20000, 6
+    X, y = orc.synthetic_problem(N, d)
+    Xc = orc.synthetic_candidates(M, d)
+    bounds = [(0.0, 1.0)] * d
+    pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5] * d, 1.7, 0.0, bounds, Xc, batch_size=bs, n_tries=3, seed=4)
+    corr_raw = np.full(d, -2 * np.log(0.5))
+    Ki = np.linalg.inv(1.7 * orc.corr("Matern52", corr_raw, X, X))
+    var = 1.0 / np.diag(Ki)
+    nes = orc.nes_error(y - (Ki @ y) * var, var, y)
+    ge = orc.fit(X, nes, "Matern52", theta[:d], float(np.exp(theta[d])), "adaptive")
+    oi, ov, _ = orc.pei_batch_argmax(ge, "Matern52", Xc, pseudopoints(X, bounds), float(nes.max()), bs)
+    assert gidx.tolist() == oi.tolist()
+    assert np.allclose(vals, ov, rtol=1e-6)
+
+
+def test_c_abi_error_codes(exq):
+    """Bad arguments and wrong call order come back as negative codes with a message, never a crash."""
+    import ctypes as C
+
+    from exauq_toolbox_b200 import _lib
+
+    lib = _lib.load()
+    X = np.random.default_rng(0).uniform(0, 1, (10, 2))
+    y = X[:, 0]
+    dp = C.POINTER(C.c_double)
+    h = C.c_void_p()
+    assert lib.exq_gp_create(0, 2, X.ctypes.data_as(dp), y.ctypes.data_as(dp), 0, C.byref(h)) == _lib.EXQ_ERR_ARG
+    assert lib.exq_gp_create(10, 2, X.ctypes.data_as(dp), y.ctypes.data_as(dp), 7, C.byref(h)) == _lib.EXQ_ERR_ARG
+    assert b"kernel" in lib.exq_last_error()
+    assert lib.exq_gp_create(10, 2, X.ctypes.data_as(dp), y.ctypes.data_as(dp), 0, C.byref(h)) == 0
+    out = np.empty(10)
+    assert lib.exq_gp_predict(h, X.ctypes.data_as(dp), 10, out.ctypes.data_as(dp), out.ctypes.data_as(dp)) == _lib.EXQ_ERR_STATE
+    assert lib.exq_gp_loo(h, out.ctypes.data_as(dp), out.ctypes.data_as(dp), out.ctypes.data_as(dp)) == _lib.EXQ_ERR_STATE
+    raw = np.full(2, 2.4)          # length scale 0.3
+    assert lib.exq_gp_fit(h, raw.ctypes.data_as(dp), -1.0, 0.0, 0, None, None, None) == _lib.EXQ_ERR_ARG
+    assert lib.exq_gp_fit(h, raw.ctypes.data_as(dp), 1.0, 0.0, 0, None, None, None) == 0
+    assert lib.exq_gp_predict(h, X.ctypes.data_as(dp), 10, out.ctypes.data_as(dp), None) == 0
+    assert np.allclose(out, y, atol=1e-7)
+    assert lib.exq_gp_destroy(h) == 0
+    with pytest.raises(ValueError):
+        exq.DeviceGP(X, y[:5], "Matern52")
+    with pytest.raises(KeyError):
+        exq.DeviceGP(X, y, "Cubic")
