@@ -180,7 +180,7 @@ def test_c_abi_error_codes(exq):
 
     lib = _lib.load()
     X = np.random.default_rng(0).uniform(0, 1, (10, 2))
-    y = X[:, 0]
+    y = np.ascontiguousarray(X[:, 0])      # raw ctypes calls need contiguous buffers
     dp = C.POINTER(C.c_double)
     h = C.c_void_p()
     assert lib.exq_gp_create(0, 2, X.ctypes.data_as(dp), y.ctypes.data_as(dp), 0, C.byref(h)) == _lib.EXQ_ERR_ARG
