@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--batch-size", type=int, default=16)
     ap.add_argument("--restarts", type=int, default=15, help="MAP restarts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --candidates and --restarts are per GPU; strong: they are totals split over the GPUs")
     return ap.parse_args()
 
 
@@ -335,7 +337,7 @@ def run_b200(a):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_per_step, "design_batch_s": ms_per_step * 1e-3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "kernels": other,
         "map_fit": {"evals_per_step_per_gpu": map_evals, "batched_rounds_per_step": map_batches},
@@ -357,12 +359,21 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def apply_scaling(a):
+    """strong scaling: one fixed design batch (1e6 candidates, 15 restarts in total) split over the ranks"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.scaling == "strong" and world > 1:
+        a.candidates = (a.candidates + world - 1) // world
+        a.restarts = (a.restarts + world - 1) // world
+    return a
+
+
 def main():
     # keep stdout clean for the ONE JSON line: libraries (NCCL banner, ...) print to fd 1
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
-    a = parse_args()
+    a = apply_scaling(parse_args())
     if a.impl == "reference":
         run_reference(a)
     else:
