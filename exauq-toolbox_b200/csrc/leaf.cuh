@@ -154,78 +154,103 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
         }
         __syncthreads();
         LEAF_TICK(2);
-        // (c) rank-8 update of every trailing tile, in registers
-#pragma unroll
-        for (int s = 0; s < LEAF_SLOTS; s++) {
-            if (tb[s] < 0) continue;
-            const int bi = tb[s] >> 8, bj = tb[s] & 255;
-            if (bj <= p) continue;
-            double a0 = S[(8 * bi + g) * LEAF_LD + j0 + t];
-            double a1 = S[(8 * bi + g) * LEAF_LD + j0 + 4 + t];
-            double b0 = S[(8 * bj + g) * LEAF_LD + j0 + t];
-            double b1 = S[(8 * bj + g) * LEAF_LD + j0 + 4 + t];
-            dmma884(c[s][0], c[s][1], -a0, b0);
-            dmma884(c[s][0], c[s][1], -a1, b1);
-            if (bj == p + 1) {
-                int row = 8 * bi + g, col = 8 * bj + 2 * t;
-                S[row * LEAF_LD + col] = c[s][0];
-                S[row * LEAF_LD + col + 1] = c[s][1];
+        // (c) rank-8 update of every trailing tile, in registers.  Tiles are enumerated column-major,
+        // so the tiles with bj > p are a contiguous SUFFIX of this warp's slots: enter the unrolled
+        // slot sequence at the first active one (no per-slot branch, loads and DMMAs of successive
+        // slots overlap).
+        {
+            const int q0 = 16 * (p + 1) - ((p + 1) * p) / 2;          // first tile of block column p+1
+            const int q1 = 16 * (p + 2) - ((p + 2) * (p + 1)) / 2;    // first tile of block column p+2
+            const int smin = (q0 - warp + 7) >> 3;
+#define LEAF_SLOT_UPDATE(SL)                                                              \
+    if (tb[SL] >= 0) {                                                                    \
+        const int bi = tb[SL] >> 8, bj = tb[SL] & 255;                                    \
+        double a0 = S[(8 * bi + g) * LEAF_LD + j0 + t];                                   \
+        double a1 = S[(8 * bi + g) * LEAF_LD + j0 + 4 + t];                               \
+        double b0 = S[(8 * bj + g) * LEAF_LD + j0 + t];                                   \
+        double b1 = S[(8 * bj + g) * LEAF_LD + j0 + 4 + t];                               \
+        dmma884(c[SL][0], c[SL][1], -a0, b0);                                             \
+        dmma884(c[SL][0], c[SL][1], -a1, b1);                                             \
+        if (warp + 8 * SL < q1) {                                                         \
+            int row = 8 * bi + g, col = 8 * bj + 2 * t;                                   \
+            S[row * LEAF_LD + col] = c[SL][0];                                            \
+            S[row * LEAF_LD + col + 1] = c[SL][1];                                        \
+        }                                                                                 \
+    }
+            switch (smin < 0 ? 0 : smin) {
+                case 0: LEAF_SLOT_UPDATE(0)
+                case 1: LEAF_SLOT_UPDATE(1)
+                case 2: LEAF_SLOT_UPDATE(2)
+                case 3: LEAF_SLOT_UPDATE(3)
+                case 4: LEAF_SLOT_UPDATE(4)
+                case 5: LEAF_SLOT_UPDATE(5)
+                case 6: LEAF_SLOT_UPDATE(6)
+                case 7: LEAF_SLOT_UPDATE(7)
+                case 8: LEAF_SLOT_UPDATE(8)
+                case 9: LEAF_SLOT_UPDATE(9)
+                case 10: LEAF_SLOT_UPDATE(10)
+                case 11: LEAF_SLOT_UPDATE(11)
+                case 12: LEAF_SLOT_UPDATE(12)
+                case 13: LEAF_SLOT_UPDATE(13)
+                case 14: LEAF_SLOT_UPDATE(14)
+                case 15: LEAF_SLOT_UPDATE(15)
+                case 16: LEAF_SLOT_UPDATE(16)
+                default: break;
             }
+#undef LEAF_SLOT_UPDATE
         }
         __syncthreads();
         LEAF_TICK(3);
     }
 
     // ================= phase 2: Linv = L^-1 ==============================================
-    // Y_ij = sum_{k=j}^{i-1} L_ik X_kj accumulates in registers; X_ij = -X_ii Y_ij.
-#pragma unroll
-    for (int s = 0; s < LEAF_SLOTS; s++) c[s][0] = c[s][1] = 0.0;
+    // Block column j of X = L^-1 depends only on L and on the diagonal inverses XD:
+    //   X_jj = XD_j,   X_ij = -XD_i * sum_{k=j}^{i-1} L_ik X_kj   (i > j),
+    // so each warp solves its own block columns {w, 15 - w} (17 block rows in total for every
+    // warp) with no block-wide barrier; finished X_kj tiles are parked TRANSPOSED in the strictly
+    // upper part of S, where the same warp reads them back as DMMA B fragments.
     double* my_scratch = scratch + warp * 8 * LEAF_XD_LD;
-    for (int k = 0; k < LEAF_NBLK; k++) {
-        // (1) finalise block row k
-#pragma unroll
-        for (int s = 0; s < LEAF_SLOTS; s++) {
-            if (tb[s] < 0) continue;
-            const int bi = tb[s] >> 8, bj = tb[s] & 255;
-            if (bi != k || bj >= k) continue;
-            my_scratch[g * LEAF_XD_LD + 2 * t] = c[s][0];
-            my_scratch[g * LEAF_XD_LD + 2 * t + 1] = c[s][1];
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        const int j = half ? (LEAF_NBLK - 1 - warp) : warp;
+#pragma unroll 1
+        for (int i = j + 1; i < LEAF_NBLK; i++) {
+            // Y = sum_k L_ik X_kj, two independent accumulators (even / odd k)
+            double y0[2] = {0.0, 0.0}, y1[2] = {0.0, 0.0};
+            {
+                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * j + t];
+                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * j + 4 + t];
+                const double b0 = XD[(j * 8 + t) * LEAF_XD_LD + g];
+                const double b1 = XD[(j * 8 + 4 + t) * LEAF_XD_LD + g];
+                dmma884(y0[0], y0[1], a0, b0);
+                dmma884(y1[0], y1[1], a1, b1);
+            }
+#pragma unroll 2
+            for (int k = j + 1; k < i; k++) {
+                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * k + t];
+                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * k + 4 + t];
+                const double b0 = S[(8 * j + g) * LEAF_LD + 8 * k + t];
+                const double b1 = S[(8 * j + g) * LEAF_LD + 8 * k + 4 + t];
+                dmma884(y0[0], y0[1], a0, b0);
+                dmma884(y1[0], y1[1], a1, b1);
+            }
+            // X_ij = -XD_i * Y : Y goes through scratch to become a B fragment
+            my_scratch[g * LEAF_XD_LD + 2 * t] = y0[0] + y1[0];
+            my_scratch[g * LEAF_XD_LD + 2 * t + 1] = y0[1] + y1[1];
             __syncwarp();
-            double b0 = my_scratch[t * LEAF_XD_LD + g];
-            double b1 = my_scratch[(4 + t) * LEAF_XD_LD + g];
-            double a0 = XD[(k * 8 + g) * LEAF_XD_LD + t];
-            double a1 = XD[(k * 8 + g) * LEAF_XD_LD + 4 + t];
+            const double b0 = my_scratch[t * LEAF_XD_LD + g];
+            const double b1 = my_scratch[(4 + t) * LEAF_XD_LD + g];
+            const double a0 = XD[(i * 8 + g) * LEAF_XD_LD + t];
+            const double a1 = XD[(i * 8 + g) * LEAF_XD_LD + 4 + t];
             double d0 = 0.0, d1 = 0.0;
             dmma884(d0, d1, -a0, b0);
             dmma884(d0, d1, -a1, b1);
-            // X[8k+g][8bj+2t(+1)] stored transposed
-            S[(8 * bj + 2 * t) * LEAF_LD + 8 * k + g] = d0;
-            S[(8 * bj + 2 * t + 1) * LEAF_LD + 8 * k + g] = d1;
+            S[(8 * j + 2 * t) * LEAF_LD + 8 * i + g] = d0;
+            S[(8 * j + 2 * t + 1) * LEAF_LD + 8 * i + g] = d1;
             __syncwarp();
         }
-        __syncthreads();
-        LEAF_TICK(4);
-        // (2) Y_ij += L_ik X_kj for i > k >= j
-#pragma unroll
-        for (int s = 0; s < LEAF_SLOTS; s++) {
-            if (tb[s] < 0) continue;
-            const int bi = tb[s] >> 8, bj = tb[s] & 255;
-            if (bi <= k || bj > k) continue;
-            double a0 = S[(8 * bi + g) * LEAF_LD + 8 * k + t];
-            double a1 = S[(8 * bi + g) * LEAF_LD + 8 * k + 4 + t];
-            double b0, b1;
-            if (bj == k) {
-                b0 = XD[(k * 8 + t) * LEAF_XD_LD + g];
-                b1 = XD[(k * 8 + 4 + t) * LEAF_XD_LD + g];
-            } else {
-                b0 = S[(8 * bj + g) * LEAF_LD + 8 * k + t];
-                b1 = S[(8 * bj + g) * LEAF_LD + 8 * k + 4 + t];
-            }
-            dmma884(c[s][0], c[s][1], a0, b0);
-            dmma884(c[s][0], c[s][1], a1, b1);
-        }
-        LEAF_TICK(5);
     }
+    LEAF_TICK(5);
     __syncthreads();
 
     // ---- write back L (upper zeroed) and Linv (full tile, zeros above the diagonal) ----
