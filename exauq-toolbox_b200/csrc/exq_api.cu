@@ -864,6 +864,22 @@ int exq_gp_kinv(exq_gp_t gp, double* out) {
     rc = upload_theta(tmp, th);
     if (!rc) rc = assemble_and_factor(tmp, gp->X, 0, N, gp->kernel_id, info);
     if (!rc && info[0] != 0) rc = fail(EXQ_NOT_PD, "Covariance Matrix is, or too close to singular.");
+    if (!rc) {
+        // cond_2(K) >= (max L_ii / min L_ii)^2: when even this lower bound reaches 1/eps the reference's
+        // check (np.linalg.cond(k) >= 1/eps, exauq/core/modelling.py:1082-1093) would refuse the matrix
+        std::vector<double> diag(N);
+        cudaError_t e = cudaMemcpy2DAsync(diag.data(), sizeof(double), tmp.A, (size_t)(tmp.Np + 1) * sizeof(double),
+                                          sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, g.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_kinv: ") + cudaGetErrorString(e));
+        if (!rc) {
+            double lo = diag[0], hi = diag[0];
+            for (int i = 1; i < N; i++) { lo = std::min(lo, diag[i]); hi = std::max(hi, diag[i]); }
+            const double ratio = hi / lo;
+            if (!(lo > 0.0) || ratio * ratio >= 1.0 / 2.220446049250313e-16)
+                rc = fail(EXQ_NOT_PD, "Covariance Matrix is, or too close to singular.");
+        }
+    }
     if (!rc) rc = lauum(tmp);
     if (!rc) {
         cudaError_t e = cudaMemcpy2DAsync(out, (size_t)N * sizeof(double), tmp.W, (size_t)tmp.Np * sizeof(double),

@@ -179,3 +179,20 @@ def test_pei_candidates_matches_reference_peicalculator(api):
         ref_vals = np.array([pei.compute(api.Input(*x)) for x in Xc])
     assert idx.tolist() == chosen
     assert np.allclose(cand.download("pei"), ref_vals, rtol=1e-7, atol=1e-13 * np.max(val))
+
+
+def test_kinv_raises_value_error_for_singular_covariance(api):
+    """exauq/core/modelling.py:1082-1113: a (numerically) singular covariance makes kinv raise
+    ValueError('Cannot compute covariance inverse: ...'); here at first access (kinv is lazy)."""
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, (30, 2))
+    data = [api.TrainingDatum(api.Input(*x), float(x[0])) for x in X]
+    gp = api.B200GaussianProcess(kernel="SquaredExponential", nugget=1e-6)
+    # very long length scales: cov * C is singular to working precision without the nugget
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters([50.0, 50.0], 1.0, 1e-6))
+    with pytest.raises(ValueError, match="Cannot compute covariance inverse"):
+        _ = gp.kinv
+    good = api.B200GaussianProcess(kernel="Matern52")
+    good.fit(data, hyperparameters=api.GaussianProcessHyperparameters([0.3, 0.3], 1.0, 0.0))
+    k = good.covariance_matrix([d.input for d in data])
+    assert np.allclose(good.kinv @ k, np.eye(30), atol=1e-8)
