@@ -159,6 +159,16 @@ def cpu_port_sample(a, X, y, Xc, n_refits=1, n_cand=1024, full_grad_terms=1):
     return M / batch_s, t, sample
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -177,6 +187,7 @@ def run_reference(a):
         return
     from oracle import gp_oracle as orc
 
+    use_all_host_threads()
     X, y = orc.synthetic_problem(a.n_train, a.dim)
     Xc = orc.synthetic_candidates(4096, a.dim)
     vals, times = [], []
@@ -347,6 +358,7 @@ def run_b200(a):
     if world == 1 and not a.no_cpu_baseline:
         from oracle import gp_oracle as orc  # checker / CPU baseline leg only
 
+        use_all_host_threads()
         v, parts, sample = cpu_port_sample(a, X, y, orc.synthetic_candidates(4096, d))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample,
                                 "parts": parts}
