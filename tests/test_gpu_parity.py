@@ -243,3 +243,44 @@ def test_full_size_properties(exq, orc):
     assert relerr(dev.neg_log_likelihood, orc.neg_log_likelihood(o)) < 1e-9
     mo, vo = orc.predict(o, Xc[:200])
     assert close(m1[:200], mo) and close(v1[:200], vo)
+
+
+def test_randomised_shapes_and_hyperparameters(exq, orc):
+    """Seeded sweep over N (1..600, incl. non-multiples of the 64/128 tiles), d (1..11, odd and even),
+    kernels, length scales and nuggets: fit / predict / LOO / log-likelihood+gradient / PEI vs the oracle."""
+    rng = np.random.default_rng(2024)
+    kernels = ["Matern52", "SquaredExponential", "ProductMat52"]
+    for case in range(14):
+        N = int(rng.choice([2, 3, 17, 63, 64, 65, 129, 200, 257, 383, 600]))
+        d = int(rng.integers(1, 12))
+        kernel = kernels[case % 3]
+        X = rng.uniform(0, 1, (N, d))
+        y = np.sin(3 * X).sum(axis=1) + 0.1 * rng.standard_normal(N)
+        ell = rng.uniform(0.15, 0.6, d) if kernel != "SquaredExponential" else rng.uniform(0.08, 0.25, d)
+        cov = float(rng.uniform(0.3, 3.0))
+        nug = float(rng.choice([0.0, 1e-8, 1e-4])) if kernel != "SquaredExponential" else 1e-6
+        corr_raw = -2 * np.log(ell)
+        dev = exq.DeviceGP(X, y, kernel).fit(corr_raw, cov, nug)
+        o = orc.fit(X, y, kernel, corr_raw, cov, nug)
+        tag = f"case {case}: N={N} d={d} {kernel} nug={nug}"
+        assert relerr(dev.neg_log_likelihood, orc.neg_log_likelihood(o)) < 1e-9, tag
+        Xc = rng.uniform(0, 1, (int(rng.integers(1, 300)), d))
+        m, v = dev.predict(Xc)
+        mo, vo = orc.predict(o, Xc)
+        assert close(m, mo) and close(v, vo), tag
+        if N >= 2:
+            idx = np.unique(rng.integers(0, N, 4))
+            lm, lv, ln = dev.loo()
+            om, ov, on = orc.loo_refit(X, y, kernel, corr_raw, cov, nug, idx)
+            assert close(lm[idx], om) and close(lv[idx], ov) and close(ln[idx], on, rel=1e-7), tag
+        th = np.concatenate([corr_raw, [np.log(cov)]])[None, :] + rng.uniform(-0.2, 0.2, (2, d + 1))
+        val, grad, info, _ = dev.logpost_batch(th, nug)
+        for r in range(2):
+            ov_, og = orc.neg_log_likelihood_grad(X, y, kernel, th[r], nug)
+            assert info[r] == 0 and relerr(val[r], ov_) < 1e-9, tag
+            assert np.allclose(grad[r], og, rtol=1e-6, atol=1e-7 * max(1.0, np.max(np.abs(og)))), tag
+        rep = rng.uniform(0, 1, (int(rng.integers(0, 9)), d))
+        cand = exq.DeviceCandidates(Xc)
+        cand.pei_eval(dev, rep, float(y.max()))
+        po = orc.pei(o, kernel, Xc, rep, float(y.max()))
+        assert np.allclose(cand.download("pei"), po, rtol=1e-6, atol=1e-13 * max(np.max(np.abs(po)), 1e-300)), tag
