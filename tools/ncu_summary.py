@@ -53,10 +53,11 @@ def main():
             lines += [f"## launch list ({tag}; `--metrics gpu__time_duration.sum`, cold-cache and serialised: compare shares)", ""]
             lines += launch_table(p) + [""]
     reps = [("variance GEMM Z = Linv Kc^T, Np=4096, Mc=32768 -- FINAL (cp.async interleaved, fragments double-buffered across k-tiles, grouped raster)", "prof_gemm_predict_r01_final.ncu-rep"),
-            ("LAUUM / factor GEMM (late launch of logpost_batch) -- FINAL", "prof_gemm_lauum_r01_final.ncu-rep"),
+            ("last three GEMM launches of logpost_batch R=4: top-level trtri merge x2 and LAUUM -- FINAL", "prof_gemm_lauum_r01_final.ncu-rep"),
             ("cross-covariance assembly, 128x64 tile, 2 CTAs/SM -- FINAL", "prof_assemble_r01_final.ncu-rep"),
             ("leaf potrf+trtri 128x128 -- FINAL", "prof_leaf_r01_final.ncu-rep"),
-            ("per-candidate epilogue (mean, variance, repulsion, EI)", "prof_finalize_r01_final.ncu-rep"),
+            ("per-candidate epilogue (mean, variance, repulsion, EI) -- FINAL (16-byte loads, 3-op division)", "prof_finalize_r01_final.ncu-rep"),
+            ("PEI update + arg max over 131072 candidates -- FINAL", "prof_update_r01_final.ncu-rep"),
             ("variance GEMM, grouped raster, burst cp.async (second version)", "prof_gemm_predict_r01b.ncu-rep"),
             ("variance GEMM, 2-D raster (first version)", "prof_gemm_predict_r01.ncu-rep"),
             ("cross-covariance assembly, 128x128 tile, 1 CTA/SM (first version)", "prof_assemble_r01.ncu-rep"),
@@ -70,9 +71,10 @@ def main():
         if not ms:
             continue
         lines.append(f"### {title}")
-        for k, v in ms[0].items():
-            lines.append(f"- {k}: {v}")
-        lines.append("")
+        for m in ms[:3]:
+            for k, v in m.items():
+                lines.append(f"- {k}: {v}")
+            lines.append("")
     lines += ["## reading", "",
               "* Variance GEMM: algorithmic bytes per launch 8*(Mc*Np + Np^2/2) = 1.14 GB.  The first 2-D raster re-read the KcT chunk once per",
               "  row tile (17.8 GB DRAM reads, L2 hit 46 %); the grouped raster (8 candidate tiles x all row tiles) brings it to ~3.3 GB (L2 hit 84 %).",
