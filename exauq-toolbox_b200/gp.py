@@ -624,16 +624,197 @@ class _Rendezvous:
         self._thread.join()
 
 
+class _LbfgsbStepper:
+    """scipy's L-BFGS-B (``scipy.optimize._lbfgsb_py._minimize_lbfgsb`` with its default options, which
+    is what ``minimize(..., method="L-BFGS-B")`` at exauq/utilities/mogp_fitting.py:318-324 runs) driven
+    through its reverse-communication core ``_lbfgsb.setulb``: ``advance()`` runs the optimiser until it
+    asks for the objective and gradient at ``self.x`` ("FG") or stops ("DONE"); ``feed(f, g)`` hands them
+    over.  Same routine, same inputs, same iterates as ``minimize`` -- but the caller decides WHEN the
+    objective is evaluated, so all restarts of a round share one batched device call without one
+    Python thread per restart."""
+
+    MAXCOR, FTOL, GTOL, MAXFUN, MAXITER, MAXLS = 10, 2.220446049250313e-09, 1e-05, 15000, 15000, 20
+
+    def __init__(self, setulb, x0, bounds):
+        n = len(x0)
+        self._setulb = setulb
+        self.m = self.MAXCOR
+        self.factr = self.FTOL / np.finfo(float).eps
+        int_dtype = np.int32
+        try:
+            from scipy.optimize._lbfgsb_py import HAS_ILP64
+
+            int_dtype = np.int64 if HAS_ILP64 else np.int32
+        except ImportError:
+            pass
+        self.nbd = np.zeros(n, dtype=int_dtype)
+        self.low = np.zeros(n, dtype=np.float64)
+        self.up = np.zeros(n, dtype=np.float64)
+        x0 = np.asarray(x0, dtype=np.float64).ravel()
+        if bounds is not None:
+            if len(bounds) != n:
+                raise ValueError("length of x0 != length of bounds")
+            lb = np.array([-np.inf if b[0] is None else float(b[0]) for b in bounds])
+            ub = np.array([np.inf if b[1] is None else float(b[1]) for b in bounds])
+            if (lb > ub).any():
+                raise ValueError("LBFGSB - one of the lower bounds is greater than an upper bound.")
+            x0 = np.clip(x0, lb, ub)
+            code = {(False, False): 0, (True, False): 1, (True, True): 2, (False, True): 3}
+            for k in range(n):
+                has_l, has_u = not np.isinf(lb[k]), not np.isinf(ub[k])
+                if has_l:
+                    self.low[k] = lb[k]
+                if has_u:
+                    self.up[k] = ub[k]
+                self.nbd[k] = code[(has_l, has_u)]
+        m = self.m
+        self.x = np.array(x0, dtype=np.float64)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros((n,), dtype=np.float64)
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=int_dtype)
+        self.task = np.zeros(2, dtype=int_dtype)
+        self.ln_task = np.zeros(2, dtype=int_dtype)
+        self.lsave = np.zeros(4, dtype=int_dtype)
+        self.isave = np.zeros(44, dtype=int_dtype)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.n_iterations = 0
+        self.nfev = 0
+
+    def advance(self) -> str:
+        while True:
+            self.g = np.asarray(self.g, dtype=np.float64)
+            self._setulb(self.m, self.x, self.low, self.up, self.nbd, self.f, self.g, self.factr, self.GTOL, self.wa,
+                         self.iwa, self.task, self.lsave, self.isave, self.dsave, self.MAXLS, self.ln_task)
+            if self.task[0] == 3:
+                return "FG"
+            if self.task[0] == 1:
+                self.n_iterations += 1
+                if self.n_iterations >= self.MAXITER:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > self.MAXFUN:
+                    self.task[0], self.task[1] = 5, 502
+                continue
+            return "DONE"
+
+    def feed(self, f: float, g: np.ndarray):
+        self.f = np.float64(f)
+        self.g = np.array(g, dtype=np.float64)
+        self.nfev += 1
+
+
+def _get_setulb():
+    """scipy's private reverse-communication entry point, or None when this scipy lays it out differently."""
+    try:
+        import inspect
+
+        from scipy.optimize import _lbfgsb
+        from scipy.optimize._lbfgsb_py import _minimize_lbfgsb
+
+        if "ln_task" not in inspect.getsource(_minimize_lbfgsb):
+            return None
+        return _lbfgsb.setulb
+    except Exception:
+        return None
+
+
+def _run_map_restarts_lockstep(setulb, dev, priors, starts, raw_bounds, nugget, adaptive, fit_nugget, stats):
+    """All restarts advance in lock step in ONE thread; each round is one batched device call."""
+    n = len(starts)
+    steppers: list = [None] * n
+    out: list = [None] * n
+    active = []
+    for i, s0 in enumerate(starts):
+        try:
+            steppers[i] = _LbfgsbStepper(setulb, s0, raw_bounds)
+            active.append(i)
+        except ValueError:
+            raise
+    n_batches = n_evals = 0
+    gpu_s = 0.0
+    last_eval: dict[int, bytes] = {}
+    while active:
+        need = []
+        for i in list(active):
+            st = steppers[i]
+            status = st.advance()
+            # the first request repeats x0, which minimize() has already evaluated once (ScalarFunction
+            # caches it); evaluating it here once is the same single evaluation
+            if status == "FG":
+                key = st.x.tobytes()
+                if last_eval.get(i) == key:      # same point asked twice: feed the cached values back
+                    st.feed(st.f, st.g)
+                    need_again = True
+                    while need_again:
+                        status = st.advance()
+                        need_again = status == "FG" and last_eval.get(i) == st.x.tobytes()
+                        if need_again:
+                            st.feed(st.f, st.g)
+                    if status == "DONE":
+                        out[i] = (float(st.f), np.array(st.x))
+                        active.remove(i)
+                        continue
+                need.append(i)
+            else:
+                out[i] = (float(st.f), np.array(st.x))
+                active.remove(i)
+        if not need:
+            break
+        ok = []
+        for i in need:
+            with np.errstate(over="ignore"):
+                finite = np.all(np.isfinite(np.exp(steppers[i].x)))
+            if finite:
+                ok.append(i)
+            else:                                     # FloatingPointError in the reference: restart skipped
+                out[i] = None
+                active.remove(i)
+        if not ok:
+            continue
+        thetas = np.array([steppers[i].x for i in ok])
+        t0 = time.perf_counter()
+        if fit_nugget:
+            val, grad, info, _ = dev.logpost_batch(thetas, nugget, adaptive, fit_nugget=True)
+        else:
+            val, grad, info, _ = dev.logpost_batch(thetas, nugget, adaptive)
+        gpu_s += time.perf_counter() - t0
+        n_batches += 1
+        n_evals += len(ok)
+        for k, i in enumerate(ok):
+            if info[k] != 0 or not np.isfinite(val[k]):   # LinAlgError in the reference: restart skipped
+                out[i] = None
+                active.remove(i)
+                continue
+            theta = steppers[i].x
+            steppers[i].feed(float(val[k] - priors.logp(theta)), grad[k] - priors.dlogp_draw(theta))
+            last_eval[i] = theta.tobytes()
+    if stats is not None:
+        stats.update(batches=n_batches, evals=n_evals, gpu_s=gpu_s)
+    return out
+
+
 def run_map_restarts(dev, priors: MapPriors, starts, raw_bounds, nugget: float, adaptive: bool,
-                     stats: Optional[dict] = None, return_all: bool = False, fit_nugget: bool = False):
+                     stats: Optional[dict] = None, return_all: bool = False, fit_nugget: bool = False,
+                     lockstep: bool = True):
     """One scipy L-BFGS-B minimisation per starting point, as the restart loop of
-    ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:309-335); each optimiser runs in
-    its own thread and all objective/gradient requests of a round are evaluated in one
-    batched GPU call.  Restarts that hit a non-positive-definite covariance or a floating
+    ``_fit_single_GP_MAP`` (exauq/utilities/mogp_fitting.py:309-335), with all objective/gradient
+    requests of a round evaluated in one batched GPU call.  Default: the optimisers are stepped in
+    lock step through scipy's reverse-communication core (``_LbfgsbStepper``); if this scipy does not
+    expose it in the expected form (or ``lockstep=False``), each ``minimize`` call runs in its own
+    thread and the requests rendezvous (``_Rendezvous``).  Restarts that hit a non-positive-definite covariance or a floating
     point overflow are skipped (:332-335).  Returns the raw parameters with the lowest
     negative log-posterior, or None if every restart failed (``return_all``: the list of
     ``(value, theta)`` / ``None`` per start instead)."""
     d = dev.d
+    setulb = _get_setulb() if lockstep else None
+    if setulb is not None:
+        out = _run_map_restarts_lockstep(setulb, dev, priors, starts, raw_bounds, nugget, adaptive, fit_nugget, stats)
+        if return_all:
+            return out
+        done = [o for o in out if o is not None]
+        if not done:
+            return None
+        return done[int(np.argmin(np.array([o[0] for o in done])))][1]
     rv = _Rendezvous(dev, len(starts), nugget, adaptive, fit_nugget)
     out: list[Optional[tuple[float, np.ndarray]]] = [None] * len(starts)
 
