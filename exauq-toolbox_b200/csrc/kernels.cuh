@@ -20,6 +20,9 @@ namespace exq {
 // Point tiles (128 points x d, contiguous) are staged with one TMA bulk copy each.
 // =====================================================================================
 constexpr int GRAD_XT_LD = 132;
+#ifndef EXQ_ASM_MIN_CTAS
+#define EXQ_ASM_MIN_CTAS 2
+#endif
 constexpr int ASM_THREADS = 256;
 constexpr int ASM_BN = 64;          // CTA tile: 128 rows x 64 columns, 8 x 4 entries per thread
 constexpr int ASM_XT_LD = ASM_BN + 4;
@@ -35,7 +38,7 @@ struct AsmArgs {
     int scale_sigma2;      // 0: plain correlation (no sigma2, no nugget)
 };
 
-__global__ void __launch_bounds__(ASM_THREADS, 2) assemble_kernel(AsmArgs p) {
+__global__ void __launch_bounds__(ASM_THREADS, EXQ_ASM_MIN_CTAS) assemble_kernel(AsmArgs p) {
     const int it = blockIdx.y, jt = blockIdx.x;
     if (p.sym && jt * ASM_BN > it * 128 + 127) return;
     extern __shared__ __align__(16) double asm_smem[];
