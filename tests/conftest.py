@@ -14,6 +14,18 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
+    # make sure the C-ABI library exists (nvcc cross-compiles without a GPU); a stale or missing
+    # .so must never make the suite fall back to anything else
+    try:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("exq_build", os.path.join(ROOT, "exauq-toolbox_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if mod.needs_build() and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            mod.build()
+    except Exception as exc:  # the tests that need the library will say so
+        print(f"[conftest] could not build libexauq_b200.so: {exc}", file=sys.stderr)
 
 
 def load_golden(name):
