@@ -556,6 +556,8 @@ int exq_init(int device) {
     if (e != cudaSuccess || n == 0)
         return fail(EXQ_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= n) return fail(EXQ_ERR_ARG, "bad device index");
+    if (const char* e = getenv("EXQ_BLOCKING_SYNC"))
+        if (atoi(e)) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);   // sleep instead of spinning in synchronisations
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));

@@ -196,3 +196,36 @@ def test_kinv_raises_value_error_for_singular_covariance(api):
     good.fit(data, hyperparameters=api.GaussianProcessHyperparameters([0.3, 0.3], 1.0, 0.0))
     k = good.covariance_matrix([d.input for d in data])
     assert np.allclose(good.kinv @ k, np.eye(30), atol=1e-8)
+
+
+def test_unchanged_multi_level_loo_samples(api):
+    """compute_multi_level_loo_samples (exauq/core/designers.py:1184-1378), unchanged, on a
+    MultiLevelGaussianProcess of B200 GPs vs the same call on MogpEmulators (same numpy / DE seeds):
+    same level chosen and the same design point to optimiser tolerance."""
+    rng = np.random.default_rng(11)
+    d = 2
+    domain = api.SimulatorDomain([(0.0, 1.0)] * d)
+    X1, X2 = rng.uniform(0.05, 0.95, (12, d)), rng.uniform(0.05, 0.95, (7, d))
+    f1 = lambda x: x[1] + x[0] ** 2 + x[1] ** 2 - np.sqrt(2)  # noqa: E731
+    f2 = lambda x: np.sin(2 * np.pi * x[0]) + np.sin(4 * np.pi * x[0] * x[1])  # noqa: E731
+    data = api.MultiLevel([[api.TrainingDatum(api.Input(*x), float(f1(x))) for x in X1],
+                           [api.TrainingDatum(api.Input(*x), float(f2(x))) for x in X2]])
+    hps = {1: ([0.5, 0.6], 2.0, 0.0), 2: ([0.25, 0.3], 1.5, 0.0)}
+    costs = api.MultiLevel([1.0, 11.0])
+    seeds = api.MultiLevel([3, 4])
+    results = []
+    for make, hp_cls in ((lambda: api.B200GaussianProcess(kernel="Matern52"), api.GaussianProcessHyperparameters),
+                         (lambda: api.MogpEmulator(kernel="Matern52"), api.MogpHyperparameters)):
+        mlgp = api.MultiLevelGaussianProcess([make() for _ in range(2)])
+        mlgp.fit(data, hyperparameters=api.MultiLevel({k: hp_cls(*v) for k, v in hps.items()}))
+        np.random.seed(21)
+        out = api.designers.compute_multi_level_loo_samples(mlgp, domain, costs, batch_size=1, seeds=seeds)
+        np.seterr(all="warn")
+        results.append(out)
+    ours, ref = results
+    assert ours.levels == ref.levels
+    for lv in ref.levels:
+        assert len(ours[lv]) == len(ref[lv])
+        for a, b in zip(ours[lv], ref[lv]):
+            assert a in domain
+            assert np.allclose(np.array(a), np.array(b), atol=5e-3)
