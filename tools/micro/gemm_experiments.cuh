@@ -6,6 +6,12 @@
 #pragma once
 #include "../../exauq-toolbox_b200/csrc/gemm_dmma.cuh"
 namespace exq {
+// constants of the 128 x 128 configuration these variants were written against
+constexpr int GEMM_BM = 128, GEMM_STAGES = 4, GEMM_WM = 2, GEMM_WN = 4, GEMM_THREADS = 256;
+constexpr int GEMM_MF = GEMM_BM / GEMM_WM / 8, GEMM_NF = GEMM_BN / GEMM_WN / 8;
+constexpr int GEMM_LDS_MN = GEMM_BM + 4;
+constexpr int GEMM_TILE_ELEMS = GEMM_BM * GEMM_LDS_K;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * GEMM_TILE_ELEMS * (int)sizeof(double);
 // ---------------------------------------------------------------------------------------
 // Warp-specialised variant: 8 consumer warps (LDS + DMMA only) and 1 producer warp that
 // issues every cp.async of the CTA.  Stages are handed over through mbarriers
