@@ -340,18 +340,20 @@ class B200GaussianProcess(AbstractGaussianProcess):
     # ---- argument validation, as the reference ---------------------------------------------
     @staticmethod
     def _parse_training_data(training_data: Any) -> tuple[TrainingDatum]:
+        """``None`` -> empty; anything that is not a sized collection of ``TrainingDatum`` -> TypeError
+        (same message as ``MogpEmulator._parse_training_data``, exauq/core/emulators.py:330-348)."""
         if training_data is None:
-            return tuple()
-        try:
-            _ = len(training_data)
-            if not all(isinstance(x, TrainingDatum) for x in training_data):
-                raise TypeError
-            return tuple(training_data)
-        except TypeError:
-            raise TypeError(
-                f"Expected 'training_data' to be of type finite collection of TrainingDatum, "
-                f"but received {type(training_data)} instead."
-            )
+            return ()
+        bad = TypeError(
+            f"Expected 'training_data' to be of type finite collection of TrainingDatum, "
+            f"but received {type(training_data)} instead."
+        )
+        if not hasattr(training_data, "__len__"):      # e.g. generators: no finite length
+            raise bad
+        items = tuple(training_data)
+        if any(not isinstance(item, TrainingDatum) for item in items):
+            raise bad
+        return items
 
     def _validate_hyperparameter_bounds(self, hyperparameter_bounds) -> None:
         if hyperparameter_bounds is None:
@@ -365,20 +367,22 @@ class B200GaussianProcess(AbstractGaussianProcess):
 
     @staticmethod
     def _validate_bound_pair(bounds: Sequence):
-        try:
-            if not len(bounds) == 2:
-                raise ValueError(
-                    "Expected 'bounds' to be a sequence of length 2, but " f"got length {len(bounds)}."
-                )
-        except TypeError:
+        """A bound is a pair (lower, upper) of ``None`` or reals with lower <= upper
+        (messages as exauq/core/emulators.py:368-395)."""
+        if not hasattr(bounds, "__len__"):
             raise TypeError(f"Expected 'bounds' to be of type sequence, but received {type(bounds)} instead.")
-        if not all(bound is None or isinstance(bound, Real) for bound in bounds):
-            raise TypeError(
-                f"Expected each 'bound' in {bounds} to be None or of type {Real} "
-                "but one or more elements were of an unexpected type."
+        if len(bounds) != 2:
+            raise ValueError(
+                "Expected 'bounds' to be a sequence of length 2, but " f"got length {len(bounds)}."
             )
         lower, upper = bounds
-        if lower is not None and upper is not None and upper < lower:
+        for value in (lower, upper):
+            if value is not None and not isinstance(value, Real):
+                raise TypeError(
+                    f"Expected each 'bound' in {bounds} to be None or of type {Real} "
+                    "but one or more elements were of an unexpected type."
+                )
+        if None not in (lower, upper) and upper < lower:
             raise ValueError(
                 "Lower bound must be less than or equal to upper bound, but received "
                 f"lower bound = {lower} and upper bound = {upper}."
@@ -455,15 +459,15 @@ class B200GaussianProcess(AbstractGaussianProcess):
     # ------------------------------------------------------------------ correlation
     def correlation(self, inputs1: Sequence[Input], inputs2: Sequence[Input]) -> np.ndarray:
         """As ``MogpEmulator.correlation`` (exauq/core/emulators.py:495-567)."""
-        try:
-            if len(inputs1) == 0 or len(inputs2) == 0:
-                return np.array([])
-        except TypeError:
-            raise TypeError(
-                "Expected 'inputs1' and 'inputs2' to be of type sequences of Input objects, "
-                f"but received {type(inputs1)} and {type(inputs2)} instead."
-            )
-        if not (all(isinstance(x, Input) for x in inputs1) and all(isinstance(x, Input) for x in inputs2)):
+        for seq in (inputs1, inputs2):
+            if not hasattr(seq, "__len__"):
+                raise TypeError(
+                    "Expected 'inputs1' and 'inputs2' to be of type sequences of Input objects, "
+                    f"but received {type(inputs1)} and {type(inputs2)} instead."
+                )
+        if min(len(inputs1), len(inputs2)) == 0:
+            return np.array([])
+        if any(not isinstance(x, Input) for x in itertools.chain(inputs1, inputs2)):
             raise TypeError(
                 "Expected all 'inputs1' and 'inputs2' to be of type Input objects, "
                 "but one or more elements were of an unexpected type."
@@ -489,22 +493,17 @@ class B200GaussianProcess(AbstractGaussianProcess):
         against the training inputs already resident on the device (``exq_gp_cross_cov``)."""
         if not self.training_data:
             return np.array([])
-        try:
-            if len(inputs) == 0:
-                return np.array([])
-            if not all(isinstance(x, Input) for x in inputs):
-                raise TypeError
-        except TypeError:
-            if not isinstance(inputs, Sequence):
-                raise TypeError(
-                    "Expected 'inputs' to be of type sequence of Input objects, but received "
-                    f"{type(inputs)} instead."
-                ) from None
-            else:
-                raise TypeError(
-                    "Expected all elements of 'inputs' to be of type Input objects, "
-                    "but one or more elements were of an unexpected type."
-                ) from None
+        if not isinstance(inputs, Sequence) and not hasattr(inputs, "__len__"):
+            raise TypeError(
+                "Expected 'inputs' to be of type sequence of Input objects, but received " f"{type(inputs)} instead."
+            )
+        if len(inputs) == 0:
+            return np.array([])
+        if any(not isinstance(x, Input) for x in inputs):
+            raise TypeError(
+                "Expected all elements of 'inputs' to be of type Input objects, "
+                "but one or more elements were of an unexpected type."
+            )
         return self._real_state().dev.cross_cov(inputs_to_array(inputs, self._input_dim()))
 
     # ------------------------------------------------------------------ batched extras
