@@ -229,3 +229,68 @@ def test_unchanged_multi_level_loo_samples(api):
         for a, b in zip(ours[lv], ref[lv]):
             assert a in domain
             assert np.allclose(np.array(a), np.array(b), atol=5e-3)
+
+
+def test_reference_emulator_behaviours(api):
+    """Backend-agnostic behaviours the reference's own tests pin for MogpEmulator
+    (tests/unit/test_emulators.py), checked on B200GaussianProcess."""
+    import warnings
+
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 1, (18, 2))
+    f = lambda x: np.sin(3 * x[0]) + x[1] ** 2  # noqa: E731
+    data = [api.TrainingDatum(api.Input(*x), float(f(x))) for x in X]
+    HP = api.GaussianProcessHyperparameters
+
+    # interpolation with zero predictive variance at the training inputs (:811-821)
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data, hyperparameters=HP([0.4, 0.5], 1.3, 0.0))
+    for d in data[:6]:
+        p = gp.predict(d.input)
+        assert abs(p.estimate - d.output) < 1e-8 and 0.0 <= p.variance < 1e-8
+
+    # correlation depends only on the length scales, covariance = process_var * correlation (:320-407)
+    gp2 = api.B200GaussianProcess(kernel="Matern52")
+    gp2.fit(data, hyperparameters=HP([0.4, 0.5], 7.7, 1e-3))
+    xs = [api.Input(0.1, 0.9), api.Input(0.6, 0.2)]
+    tr = [d.input for d in data]
+    assert np.array_equal(gp.correlation(xs, tr), gp2.correlation(xs, tr))
+    assert np.allclose(gp2.covariance_matrix(xs), 7.7 * gp2.correlation(xs, tr), rtol=1e-14)
+    c = gp.correlation(tr, tr)
+    assert np.allclose(np.diag(c), 1.0) and np.allclose(c, c.T) and np.all((c > 0) & (c <= 1))
+
+    # nugget semantics (emulators.py:427-445): supplied nugget wins; else the constructor's float; else the method
+    g1 = api.B200GaussianProcess(kernel="Matern52", nugget=0.25)
+    g1.fit(data, hyperparameters=HP([0.4, 0.5], 1.3))
+    assert g1.fit_hyperparameters.nugget == 0.25
+    g1.fit(data, hyperparameters=HP([0.4, 0.5], 1.3, 0.5))
+    assert g1.fit_hyperparameters.nugget == 0.5
+    assert gp.fit_hyperparameters.nugget == 0.0                   # adaptive, no jitter needed
+    v_small, v_big = gp.predict(xs[0]).variance, g1.predict(xs[0]).variance
+    assert v_big > v_small                                        # predictive variance includes the nugget
+    with pytest.raises(ValueError, match="'nugget'='fit'"):
+        api.B200GaussianProcess(kernel="Matern52", nugget="fit").fit(data, hyperparameters=HP([0.4, 0.5], 1.3))
+
+    # estimation respects hyperparameter bounds (:551-583) and refits replace the data
+    np.random.seed(4)
+    gb = api.B200GaussianProcess(kernel="Matern52")
+    gb.fit(data, hyperparameter_bounds=[(0.3, 0.6), (0.2, None), (0.5, 4.0)])
+    hp = gb.fit_hyperparameters
+    assert 0.3 - 1e-9 <= hp.corr_length_scales[0] <= 0.6 + 1e-9 and hp.corr_length_scales[1] >= 0.2 - 1e-9
+    assert 0.5 - 1e-9 <= hp.process_var <= 4.0 + 1e-9
+    gb.fit(data[:9], hyperparameters=hp)
+    assert len(gb.training_data) == 9
+
+    # update() adds data in front of the old data and refits (modelling.py:988-1040)
+    gu = api.B200GaussianProcess(kernel="Matern52")
+    gu.fit(data[:10], hyperparameters=HP([0.4, 0.5], 1.3, 0.0))
+    gu.update(training_data=data[10:14], hyperparameters=HP([0.4, 0.5], 1.3, 0.0))
+    assert len(gu.training_data) == 14 and gu.training_data[:4] == tuple(data[10:14])
+    with pytest.warns(UserWarning, match="No arguments were passed"):
+        gu.update()
+
+    # fewer training points than hyperparameters: warning (:303-307)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        api.B200GaussianProcess(kernel="Matern52").fit(data[:2], hyperparameters=HP([0.4, 0.5], 1.3, 0.0))
+        assert any("Fewer training points" in str(x.message) for x in w)
