@@ -332,8 +332,16 @@ def run_b200(a):
                 "traffic": None, "launches_per_step": p["launches"] / a.steps,
                 "avg_launch_ms": p["ms"] / p["launches"], "ms_per_step": p["ms"] / a.steps}
 
+    # DRAM bytes per launch of the variance GEMM from the committed `ncu --set full` capture
+    # (profiles/ncu_summary_r01.md: dram__bytes_read.sum + dram__bytes_write.sum at Np=4096, Mc=32768);
+    # algorithmic bytes per launch are 8*(Mc*Np + Np^2/2) = 1.14e9
+    NCU_TRAFFIC = {(4096, 8): 3.370598e9 + 12.609792e6}
     kern = {"gemm_dmma_kernel[variance Z=Linv*Kc^T]": roof(prof["gemm_predict"]),
             "gemm_dmma_kernel[potrf/trtri/lauum tiles]": roof(prof["gemm_factor"])}
+    vk = kern["gemm_dmma_kernel[variance Z=Linv*Kc^T]"]
+    if vk is not None and (N, d) in NCU_TRAFFIC:
+        vk["traffic"] = NCU_TRAFFIC[(N, d)]
+        vk["algorithmic_bytes"] = 8.0 * (32768 * 4096 + 4096 * 4096 / 2)
     dominant = max((k for k in kern if kern[k]), key=lambda k: kern[k]["ms_per_step"])
     roofline = dict(kern[dominant])
     roofline.update(kernel=dominant, peak_source=peak_src,

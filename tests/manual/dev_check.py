@@ -1,6 +1,7 @@
-"""Development check run on a GPU box: CUDA path vs the oracle on small seeded cases."""
+"""Manual parity dump run on a GPU box: every entry point of the CUDA path vs the oracle on small
+seeded cases (python tests/manual/dev_check.py).  Lives under tests/ because it imports the oracle."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 from oracle import gp_oracle as orc

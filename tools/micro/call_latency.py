@@ -3,16 +3,31 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "baseline", "_ref")]
 import numpy as np
+
+
+def synthetic_problem(N, d, seed=1):
+    """LHS inputs + the bench's deterministic target (same as oracle.gp_oracle.synthetic_problem, restated
+    here because only tests/, smoke() and bench.py's CPU legs may import oracle/)."""
+    import math
+    from scipy.stats.qmc import LatinHypercube
+    X = LatinHypercube(d, seed=seed).random(N)
+    y = np.sum(np.sin(6 * np.pi * X) / np.arange(1, d + 1), axis=1) + X[:, 0] * X[:, 1 % d] - math.sqrt(2.0)
+    return X, y
+
+
+def synthetic_candidates(M, d, seed=2):
+    from scipy.stats.qmc import LatinHypercube
+    return LatinHypercube(d, seed=seed).random(M)
+
 from exauq.core.modelling import Input, TrainingDatum, GaussianProcessHyperparameters, SimulatorDomain
 from exauq.core.designers import PEICalculator
 from exauq_toolbox_b200.gp import B200GaussianProcess
-from oracle import gp_oracle as orc
 for N, d in [(50, 2), (1024, 8), (4096, 8)]:
-    X, y = orc.synthetic_problem(N, d)
+    X, y = synthetic_problem(N, d)
     data = [TrainingDatum(Input(*r), float(t)) for r, t in zip(X, y)]
     gp = B200GaussianProcess(kernel="Matern52")
     gp.fit(data, hyperparameters=GaussianProcessHyperparameters([0.5] * d, 1.7, 0.0))
-    xs = [Input(*r) for r in orc.synthetic_candidates(100, d)]
+    xs = [Input(*r) for r in synthetic_candidates(100, d)]
     train_inputs = [dt.input for dt in data]
     gp.predict(xs[0])
     t0 = time.perf_counter()

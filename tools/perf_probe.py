@@ -3,7 +3,22 @@ import os, sys, time, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
-from oracle import gp_oracle as orc
+
+
+def synthetic_problem(N, d, seed=1):
+    """LHS inputs + the bench's deterministic target (same as oracle.gp_oracle.synthetic_problem, restated
+    here because only tests/, smoke() and bench.py's CPU legs may import oracle/)."""
+    import math
+    from scipy.stats.qmc import LatinHypercube
+    X = LatinHypercube(d, seed=seed).random(N)
+    y = np.sum(np.sin(6 * np.pi * X) / np.arange(1, d + 1), axis=1) + X[:, 0] * X[:, 1 % d] - math.sqrt(2.0)
+    return X, y
+
+
+def synthetic_candidates(M, d, seed=2):
+    from scipy.stats.qmc import LatinHypercube
+    return LatinHypercube(d, seed=seed).random(M)
+
 import exauq_toolbox_b200 as exq
 from exauq_toolbox_b200 import _lib
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
@@ -11,8 +26,8 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 1000000
 R = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 _lib.init(0)
-X, y = orc.synthetic_problem(N, d)
-Xc = orc.synthetic_candidates(M, d)
+X, y = synthetic_problem(N, d)
+Xc = synthetic_candidates(M, d)
 corr_raw = np.full(d, -2 * np.log(0.5)); cov = 1.7
 NAMES = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream"]
 def report(tag, ms):
