@@ -158,7 +158,42 @@ def slas_case():
     }
 
 
+def mlgp_tutorial_case():
+    """docs/designers/tutorials/training_multi_level_gp_tutorial.md: 2-level GP, LHS seed 1 with 20 / 8 points,
+    level 1 = cheap simulator, level 2 = difference to the expensive one; predictions at (0.5, 1)."""
+    from exauq.core.modelling import MultiLevel, MultiLevelGaussianProcess
+
+    def sim_level1(x):
+        return x[1] + x[0] ** 2 + x[1] ** 2 - np.sqrt(2)
+
+    def sim_delta(x):
+        return sim_func(x) - sim_level1(x)
+
+    domain = SimulatorDomain([(0, 1), (-0.5, 1.5)])
+    d1 = [TrainingDatum(x, sim_level1(x)) for x in oneshot_lhs(domain, 20, seed=1)]
+    d2 = [TrainingDatum(x, sim_delta(x)) for x in oneshot_lhs(domain, 8, seed=1)]
+    mlgp = MultiLevelGaussianProcess([MogpEmulator(kernel="Matern52"), MogpEmulator(kernel="Matern52")])
+    np.random.seed(0)
+    mlgp.fit(MultiLevel([d1, d2]))
+    x = Input(0.5, 1)
+    preds = [mlgp.predict(x, level) for level in mlgp.levels]
+    hp = {lv: mlgp[lv].fit_hyperparameters for lv in mlgp.levels}
+    return {
+        "source": "docs/designers/tutorials/training_multi_level_gp_tutorial.md:339-349",
+        "published": {"level1": {"estimate": 0.8353095922897182, "variance": 1.168910654314459e-05},
+                      "level2": {"estimate": 0.9008758897257811, "variance": 0.6237762865894648}},
+        "numpy_seed": 0,
+        "level1": {"inputs": [list(map(float, d.input)) for d in d1], "outputs": [float(d.output) for d in d1]},
+        "level2": {"inputs": [list(map(float, d.input)) for d in d2], "outputs": [float(d.output) for d in d2]},
+        "fit": {str(lv): {"corr_length_scales": list(map(float, hp[lv].corr_length_scales)),
+                          "process_var": float(hp[lv].process_var), "nugget": float(hp[lv].nugget)} for lv in hp},
+        "predict_at": [0.5, 1.0],
+        "predictions": [{"estimate": float(p.estimate), "variance": float(p.variance)} for p in preds],
+    }
+
+
 if __name__ == "__main__":
+    dump("tutorial_mlgp.json", mlgp_tutorial_case())
     dump("tutorial_gp.json", tutorial_case())
     dump("fixed_matern_d3_n40.json", fixed_hp_case("Matern52", 40, 3, 0.5, 1.7, 0.0, 11))
     dump("fixed_sqexp_d2_n30.json", fixed_hp_case("SquaredExponential", 30, 2, 0.3, 0.8, 1e-6, 12))

@@ -294,3 +294,42 @@ def test_reference_emulator_behaviours(api):
         warnings.simplefilter("always")
         api.B200GaussianProcess(kernel="Matern52").fit(data[:2], hyperparameters=HP([0.4, 0.5], 1.3, 0.0))
         assert any("Fewer training points" in str(x.message) for x in w)
+
+
+def test_multi_level_tutorial_end_to_end(api):
+    """The two-level tutorial (training_multi_level_gp_tutorial.md) with B200 GPs: MAP estimation on the
+    GPU at both levels (same numpy seed as the golden run) and MultiLevelGaussianProcess.predict."""
+    g = load_golden("tutorial_mlgp.json")
+    data = api.MultiLevel([[api.TrainingDatum(api.Input(*x), y) for x, y in zip(g["level" + lv]["inputs"], g["level" + lv]["outputs"])]
+                           for lv in ("1", "2")])
+    mlgp = api.MultiLevelGaussianProcess([api.B200GaussianProcess(kernel="Matern52") for _ in range(2)])
+    np.random.seed(g["numpy_seed"])
+    mlgp.fit(data)
+    for lv in (1, 2):
+        hp, ref = mlgp[lv].fit_hyperparameters, g["fit"][str(lv)]
+        assert np.allclose(hp.corr_length_scales, ref["corr_length_scales"], rtol=1e-4)
+        assert np.isclose(hp.process_var, ref["process_var"], rtol=1e-4)
+    x = api.Input(*g["predict_at"])
+    pub = g["published"]
+    for level, key, ref in ((1, "level1", g["predictions"][0]), (2, "level2", g["predictions"][1])):
+        p = mlgp.predict(x, level)
+        assert abs(p.estimate - ref["estimate"]) < 1e-6 and abs(p.variance - ref["variance"]) < 1e-6
+        assert abs(p.estimate - pub[key]["estimate"]) < 1e-5 and abs(p.variance - pub[key]["variance"]) < 1e-5
+
+
+def test_single_level_tutorial_end_to_end(api):
+    """training_gp_tutorial.md:259-263, 300-302: MAP estimation on the GPU (same numpy seed as the golden
+    run) reproduces the published prediction and NES error at (0.5, 1.5)."""
+    g = load_golden("tutorial_gp.json")
+    data = [api.TrainingDatum(api.Input(*x), y) for x, y in zip(g["inputs"], g["outputs"])]
+    np.random.seed(g["numpy_seed"])
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data)
+    hp, ref = gp.fit_hyperparameters, g["fit"]
+    assert np.allclose(hp.corr_length_scales, ref["corr_length_scales"], rtol=1e-5)
+    assert np.isclose(hp.process_var, ref["process_var"], rtol=1e-5) and hp.nugget == ref["nugget"]
+    p = gp.predict(api.Input(*g["predict_at"]))
+    pub = g["published"]
+    assert abs(p.estimate - g["estimate"]) < 1e-6 and abs(p.variance - g["variance"]) < 1e-6
+    assert abs(p.estimate - pub["estimate"]) < 1e-6 and abs(p.variance - pub["variance"]) < 1e-6
+    assert abs(p.nes_error(pub["observed"]) - pub["nes_error"]) < 1e-6
