@@ -282,7 +282,14 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
     return fma(r, y, q);
 }
 
-__global__ void __launch_bounds__(256) predict_finalize_kernel(FinArgs p) {
+#ifndef EXQ_FIN_MIN_BLOCKS
+#define EXQ_FIN_MIN_BLOCKS 3
+#endif
+#ifndef EXQ_FIN_UNROLL
+#define EXQ_FIN_UNROLL 8
+#endif
+constexpr int FIN_UNROLL = EXQ_FIN_UNROLL;
+__global__ void __launch_bounds__(256, EXQ_FIN_MIN_BLOCKS) predict_finalize_kernel(FinArgs p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 8 + warp;
     if (c >= p.m_valid) return;
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(256) predict_finalize_kernel(FinArgs p) {
     const int n2 = p.N >> 1;
     const double2* row2 = reinterpret_cast<const double2*>(row);
     const double2* al2 = reinterpret_cast<const double2*>(p.alpha);
-#pragma unroll 4
+#pragma unroll FIN_UNROLL
     for (int j = lane; j < n2; j += 32) {
         double2 kv = __ldcs(row2 + j);
         double2 al = al2[j];
