@@ -141,6 +141,7 @@ struct Sys {
     double *A = nullptr, *Linv = nullptr, *W = nullptr;     // [B][Np][Np]
     double* theta = nullptr;                                // [B][d+2]
     double *tvec = nullptr, *alpha = nullptr, *dinv = nullptr, *kvec = nullptr;   // [B][Np]
+    double* tpart = nullptr;                                // [B][TRMV_T_SPLITS][2][Np] partial sums
     double* ldq = nullptr;                                  // [B][2]
     int* info = nullptr;                                    // [B]
     double *Xb = nullptr, *yb = nullptr;                    // own data (LOO refits) or null
@@ -152,7 +153,7 @@ struct Sys {
 
 void sys_free(Sys& s) {
     cudaFree(s.A); cudaFree(s.Linv); cudaFree(s.W); cudaFree(s.theta); cudaFree(s.tvec);
-    cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.ldq); cudaFree(s.info);
+    cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.tpart); cudaFree(s.ldq); cudaFree(s.info);
     cudaFree(s.Xb); cudaFree(s.yb); cudaFree(s.skip); cudaFree(s.gpartial); cudaFree(s.grad);
     s = Sys();
 }
@@ -207,6 +208,7 @@ int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
     CUDA_TRY(cudaMalloc(&s.alpha, vec));
     CUDA_TRY(cudaMalloc(&s.dinv, vec));
     CUDA_TRY(cudaMalloc(&s.kvec, vec));
+    CUDA_TRY(cudaMalloc(&s.tpart, vec * TRMV_T_SPLITS * 2));
     CUDA_TRY(cudaMalloc(&s.ldq, (size_t)B * 2 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&s.info, (size_t)B * sizeof(int)));
     CUDA_TRY(cudaMalloc(&s.grad, (size_t)B * (d + 2) * sizeof(double)));
@@ -342,10 +344,14 @@ int solve_vectors(Sys& s, const double* y, int64_t strideY, int nvalid) {
     prof_end(m);
     LAUNCH_CHECK("trmv_lower_kernel");
     m = prof_begin(EXQ_PROF_STREAM, 2.0 * s.B * s.Np * s.Np, (double)s.B * s.Np * s.Np * 4.0);
-    trmv_lower_t_kernel<<<dim3(s.Np / 32, 1, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, s.tvec, s.Np, s.alpha, s.dinv,
-                                                                      s.Np, s.Np);
+    trmv_lower_t_kernel<<<dim3(s.Np / 32, TRMV_T_SPLITS, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, s.tvec, s.Np, s.tpart,
+                                                                                  s.Np);
     prof_end(m);
     LAUNCH_CHECK("trmv_lower_t_kernel");
+    m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+    trmv_t_reduce_kernel<<<dim3((s.Np + 255) / 256, 1, s.B), 256, 0, g.stream>>>(s.tpart, s.alpha, s.dinv, s.Np, s.Np);
+    prof_end(m);
+    LAUNCH_CHECK("trmv_t_reduce_kernel");
     m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
     logdet_quad_kernel<<<s.B, 256, 0, g.stream>>>(s.A, ld, sq, y, strideY, s.alpha, s.Np, nvalid, s.ldq);
     prof_end(m);
@@ -477,6 +483,7 @@ Sys sys_view(const Sys& s, int b0, int B, int dmax) {
     if (v.W) v.W += (int64_t)b0 * sq;
     v.theta += (int64_t)b0 * (s.d + 2);
     v.tvec += (int64_t)b0 * s.Np; v.alpha += (int64_t)b0 * s.Np; v.dinv += (int64_t)b0 * s.Np; v.kvec += (int64_t)b0 * s.Np;
+    v.tpart += (int64_t)b0 * TRMV_T_SPLITS * 2 * s.Np;
     v.ldq += 2 * b0; v.info += b0; v.grad += (int64_t)b0 * (s.d + 2);
     if (v.gpartial) v.gpartial += (int64_t)b0 * nt * nt * (dmax + 2);
     return v;

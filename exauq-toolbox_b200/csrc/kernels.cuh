@@ -148,20 +148,26 @@ __global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restric
     if (lane == 0) tvec[(int64_t)blockIdx.z * strideT + i] = s;
 }
 
+// Row-split version: blockIdx.y handles rows [y*chunk, (y+1)*chunk) and writes partial sums
+// part[b][y][0][j] (alpha) and part[b][y][1][j] (dinv); trmv_t_reduce_kernel adds the splits in
+// fixed order.  (One block per 32 columns alone leaves most SMs idle for a single system.)
+constexpr int TRMV_T_SPLITS = 8;
 __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restrict__ Linv, int64_t ld,
                                                            int64_t strideL, const double* __restrict__ tvec,
-                                                           int64_t strideT, double* __restrict__ alpha,
-                                                           double* __restrict__ dinv, int64_t strideV, int Np) {
+                                                           int64_t strideT, double* __restrict__ part, int Np) {
     __shared__ double red_a[8][33], red_d[8][33];
     const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
     const int j = blockIdx.x * 32 + tx;
     const double* L = Linv + (int64_t)blockIdx.z * strideL;
     const double* tv = tvec + (int64_t)blockIdx.z * strideT;
+    const int chunk = (Np + TRMV_T_SPLITS - 1) / TRMV_T_SPLITS;
+    const int r_lo = max((int)blockIdx.y * chunk, (int)blockIdx.x * 32), r_hi = min(Np, ((int)blockIdx.y + 1) * chunk);
     double sa = 0.0, sd = 0.0;
-    for (int i = blockIdx.x * 32 + ty; i < Np; i += 8) {
+#pragma unroll 4
+    for (int i = r_lo + ty; i < r_hi; i += 8) {
         double v = (i >= j) ? L[(int64_t)i * ld + j] : 0.0;
-        sa += v * tv[i];
-        sd += v * v;
+        sa = fma(v, tv[i], sa);
+        sd = fma(v, v, sd);
     }
     red_a[ty][tx] = sa;
     red_d[ty][tx] = sd;
@@ -169,9 +175,22 @@ __global__ void __launch_bounds__(256) trmv_lower_t_kernel(const double* __restr
     if (ty == 0) {
 #pragma unroll
         for (int k = 1; k < 8; k++) { sa += red_a[k][tx]; sd += red_d[k][tx]; }
-        alpha[(int64_t)blockIdx.z * strideV + j] = sa;
-        dinv[(int64_t)blockIdx.z * strideV + j] = sd;
+        double* out = part + ((int64_t)blockIdx.z * TRMV_T_SPLITS + blockIdx.y) * 2 * Np;
+        out[j] = sa;
+        out[Np + j] = sd;
     }
+}
+
+__global__ void trmv_t_reduce_kernel(const double* __restrict__ part, double* __restrict__ alpha,
+                                     double* __restrict__ dinv, int64_t strideV, int Np) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Np) return;
+    const double* p = part + (int64_t)blockIdx.z * TRMV_T_SPLITS * 2 * Np;
+    double sa = 0.0, sd = 0.0;
+#pragma unroll
+    for (int y = 0; y < TRMV_T_SPLITS; y++) { sa += p[(int64_t)y * 2 * Np + j]; sd += p[(int64_t)y * 2 * Np + Np + j]; }
+    alpha[(int64_t)blockIdx.z * strideV + j] = sa;
+    dinv[(int64_t)blockIdx.z * strideV + j] = sd;
 }
 
 // logdet = 2 sum_{i<N} log L_ii ; quad = y^T alpha.   out[b] = {logdet, quad}
