@@ -37,6 +37,9 @@ struct Ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // batched evaluations are split over stream + side[]
+    double bm64_factor = 1e9;   // 64-row tiles (2 CTAs/SM) measured faster than 128-row tiles at every level of the
+                                // recursion (34.8 vs 36.6 ms per batched evaluation); EXQ_BM64_FACTOR=0 restores 128
+    int variance_bm = 64;       // row tile of the variance GEMM (EXQ_VARIANCE_BM)
     int eval_streams = 1;   // EXQ_EVAL_STREAMS: measured gain of 2 streams is 3 % of the MAP phase, and overlapped
                             // kernels make per-launch event timings meaningless, so the default stays 1
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -279,7 +282,7 @@ int launch_gemm(const GemmArgs& a, int batch, int cls) {
     if (a.lower_only && a.krange == KR_FULL) fl *= 0.5;          // SYRK: n^2 k
     if (a.lower_only && a.krange != KR_FULL) fl *= 1.0 / 3.0;    // LAUUM: n^3 / 3
     double tiles128 = (double)(a.M / 128) * (a.N / 128) * batch * (a.lower_only ? 0.5 : 1.0);
-    if (a.cmode != C_COLSUMSQ && tiles128 < 2.0 * std::max(1, g.sm_count))
+    if (a.cmode == C_COLSUMSQ ? g.variance_bm == 64 : tiles128 < g.bm64_factor * std::max(1, g.sm_count))
         return launch_gemm_bm<AL, BL, 64>(a, batch, cls, fl);
     return launch_gemm_bm<AL, BL, 128>(a, batch, cls, fl);
 }
@@ -378,7 +381,7 @@ int assemble_sym(Sys& s, const double* X, int64_t strideX, int nvalid, int kerne
 }
 
 int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
-    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 128) * want_chunk;
+    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 64) * want_chunk;
     if (g.kct_elems < need_k) {
         cudaFree(g.KcT);
         g.KcT = nullptr; g.kct_elems = 0;
@@ -442,7 +445,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
         if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
         }
         FinArgs f{};
-        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : Np / 128;
+        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : Np / g.variance_bm;
         f.alpha = gp->fit.alpha; f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep;
         f.N = (int)gp->N; f.Np = Np; f.d = gp->d; f.kernel_id = gp->kernel_id; f.m_valid = (int)mc;
         f.tmax = tmax; f.want_pei = want_pei;
@@ -575,6 +578,8 @@ int exq_init(int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (const char* e = getenv("EXQ_EVAL_STREAMS")) g.eval_streams = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("EXQ_BM64_FACTOR")) g.bm64_factor = atof(e);
+    if (const char* e = getenv("EXQ_VARIANCE_BM")) g.variance_bm = atoi(e) == 128 ? 128 : 64;
     CUDA_TRY(cudaEventCreate(&g.t0));
     CUDA_TRY(cudaEventCreate(&g.t1));
     g.device = device;
