@@ -336,16 +336,33 @@ def run_b200(a):
     # (profiles/ncu_summary_r01.md: dram__bytes_read.sum + dram__bytes_write.sum at Np=4096, Mc=32768);
     # algorithmic bytes per launch are 8*(Mc*Np + Np^2/2) = 1.14e9
     NCU_TRAFFIC = {(4096, 8): 3.370598e9 + 12.609792e6}
-    kern = {"gemm_dmma_kernel[variance Z=Linv*Kc^T]": roof(prof["gemm_predict"]),
+    slices = _lib.variance_slices()
+    vname = ("oz::colsumsq_kernel[variance Z=Linv*Kc^T on int8 tcgen05, %d base-256 digits]" % slices if slices
+             else "gemm_dmma_kernel[variance Z=Linv*Kc^T]")
+    kern = {vname: roof(prof["gemm_predict"]),
             "gemm_dmma_kernel[potrf/trtri/lauum tiles]": roof(prof["gemm_factor"])}
-    vk = kern["gemm_dmma_kernel[variance Z=Linv*Kc^T]"]
-    if vk is not None and (N, d) in NCU_TRAFFIC:
+    vk = kern[vname]
+    if vk is not None and slices:
+        # achieved/frac above are FP64-EQUIVALENT flops (Np^2 Mc per launch) against the FP64 DMMA peak: > 1 means
+        # faster than any FP64 tensor-core kernel can be.  The pipe actually used is the int8 tensor core:
+        p = prof["gemm_predict"]
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        i8_peak = 2.0 * peaks.get("bf16_tflops_sustained", 1430.2)
+        i8 = p["bytes"] / (p["ms"] * 1e-3) / 1e12
+        vk.update(fp64_equivalent=True, int8_tops=i8, int8_peak_tops=i8_peak, int8_frac=i8 / i8_peak,
+                  int8_peak_source="2 x MEASURED_PEAKS.json bf16_tflops_sustained (kind::i8 issues at twice the "
+                                   "kind::f16 rate on the same pipe; no measured int8 entry)",
+                  products_per_fp64_product=slices * (slices + 1) // 2)
+    elif vk is not None and (N, d) in NCU_TRAFFIC:
         vk["traffic"] = NCU_TRAFFIC[(N, d)]
         vk["algorithmic_bytes"] = 8.0 * (32768 * 4096 + 4096 * 4096 / 2)
     dominant = max((k for k in kern if kern[k]), key=lambda k: kern[k]["ms_per_step"])
     roofline = dict(kern[dominant])
     roofline.update(kernel=dominant, peak_source=peak_src,
-                    note="FP64 tensor path is mma.sync DMMA.8x8x4 (tcgen05 has no f64 kind)")
+                    note="FP64 tensor path is mma.sync DMMA.8x8x4 (tcgen05 has no f64 kind); the variance product "
+                         "runs on tcgen05 kind::i8 with exact int32 accumulation in TMEM when variance_slices > 0",
+                    variance_slices=slices)
     other = {k: v for k, v in kern.items() if k != dominant}
     for name in ("leaf", "assemble"):
         p = prof[name]

@@ -30,6 +30,7 @@ SIGNATURES = {
     "exq_shutdown": (C.c_int, []),
     "exq_last_error": (C.c_char_p, []),
     "exq_device_sm_count": (C.c_int, []),
+    "exq_variance_slices": (C.c_int, []),
     "exq_launch_count": (C.c_int64, []),
     "exq_timer_start": (C.c_int, []),
     "exq_timer_stop": (C.c_int, [_dp]),
@@ -323,3 +324,8 @@ def prof_get(cls: int):
 
 def launch_count() -> int:
     return int(load().exq_launch_count())
+
+
+def variance_slices() -> int:
+    """Base-256 digits per operand of the int8 tensor-core variance product (0: FP64 DMMA GEMM)."""
+    return int(load().exq_variance_slices())

@@ -17,6 +17,7 @@
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
 #include "leaf.cuh"
+#include "ozaki_i8.cuh"
 
 using namespace exq;
 
@@ -54,6 +55,11 @@ struct Ctx {
     // KcT[chunk][Np] and the partial column sums P[Np/128][chunk]
     double *KcT = nullptr, *P = nullptr;
     size_t kct_elems = 0, p_elems = 0;
+    // int8 tcgen05 variance path (ozaki_i8.cuh): digits per operand (EXQ_OZAKI_SLICES = 0 keeps the FP64 DMMA
+    // GEMM, 5..7 selects the number of base-256 digits; 6 = 48 bits is ~2e-12 absolute on the variance)
+    int oz_slices = 6;
+    int8_t* cand_planes = nullptr;   // [S][chunk][Np] digits of the covariance chunk
+    size_t cand_planes_bytes = 0;
 } g;
 
 int fail(int code, const std::string& msg) {
@@ -126,6 +132,9 @@ int set_kernel_attrs() {
 #undef EXQ_SET_GEMM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   LEAF_SMEM_BYTES));
+    CUDA_TRY(oz::set_attrs<5>());
+    CUDA_TRY(oz::set_attrs<6>());
+    CUDA_TRY(oz::set_attrs<7>());
     const int big = 220 * 1024;
     CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -241,6 +250,9 @@ struct exq_gp_s {
     // prediction scratch
     double *KcT = nullptr, *P = nullptr;   // views of the global scratch
     double* zsmall = nullptr;              // [8][Np] for the small-M variance path
+    int8_t* linv_planes = nullptr;         // [S][Np][Np] base-256 digits of Linv (int8 variance path), built lazily
+    int* linv_exp = nullptr;               // [Np] row exponents of Linv
+    int planes_S = 0;                      // digits held in linv_planes (0: stale)
     int64_t chunk = 0;
     double* rep = nullptr;
     int rep_cap = 0;
@@ -408,6 +420,55 @@ int64_t default_chunk(const exq_gp_t gp, int64_t Mpad) {
     return std::min(c, Mpad);
 }
 
+// ---- variance product on the int8 tensor cores (ozaki_i8.cuh) ---------------------------------
+template <int S>
+int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
+    const int Np = gp->Np;
+    if (gp->planes_S != S) {
+        // digits of Linv: once per fit
+        if (!gp->linv_exp) CUDA_TRY(cudaMalloc(&gp->linv_exp, (size_t)Np * sizeof(int)));
+        cudaFree(gp->linv_planes);
+        gp->linv_planes = nullptr;
+        CUDA_TRY(cudaMalloc(&gp->linv_planes, (size_t)S * Np * Np));
+        ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)Np * Np * (4.0 + 0.5 * S));
+        oz::row_exponent_lower_kernel<<<(Np + 7) / 8, 256, 0, g.stream>>>(gp->fit.Linv, Np, Np, gp->linv_exp);
+        oz::launch_slice<S>(gp->fit.Linv, Np, Np, Np, gp->linv_exp, 0, 1, gp->linv_planes, g.stream);
+        prof_end(m);
+        LAUNCH_CHECK("ozaki slice Linv");
+        g.launches++;
+        gp->planes_S = S;
+    }
+    const size_t need = (size_t)S * gp->chunk * Np;
+    if (g.cand_planes_bytes < need) {
+        cudaFree(g.cand_planes);
+        g.cand_planes = nullptr; g.cand_planes_bytes = 0;
+        CUDA_TRY(cudaMalloc(&g.cand_planes, need));
+        g.cand_planes_bytes = need;
+    }
+    // covariance entries lie in [0, sigma^2]: one global exponent for the candidate side
+    const int fexp = oz::scale_exponent(gp->cov);
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)mc_pad * Np * (8.0 + S));
+    oz::launch_slice<S>(gp->KcT, Np, mc_pad, Np, nullptr, fexp, 0, g.cand_planes, g.stream);
+    prof_end(m);
+    LAUNCH_CHECK("ozaki slice candidates");
+    // flops: FP64-equivalent Np^2 Mc; bytes field carries the int8 operations actually issued
+    m = prof_begin(EXQ_PROF_GEMM_PREDICT, (double)Np * Np * mc_pad,
+                   (double)Np * (Np + oz::BLK_R) * mc_pad * (S * (S + 1) / 2));
+    int rc = oz::launch_colsumsq<S>(g.cand_planes, mc_pad, fexp, gp->linv_planes, gp->linv_exp, Np, gp->P, mc_pad,
+                                    g.sm_count, g.stream);
+    prof_end(m);
+    if (rc) return fail(EXQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the int8 variance kernel");
+    LAUNCH_CHECK("oz::colsumsq_kernel");
+    return EXQ_OK;
+}
+int variance_ozaki(exq_gp_t gp, int mc_pad) {
+    switch (g.oz_slices) {
+        case 5: return variance_ozaki_s<5>(gp, mc_pad);
+        case 7: return variance_ozaki_s<7>(gp, mc_pad);
+        default: return variance_ozaki_s<6>(gp, mc_pad);
+    }
+}
+
 // mean / var / (pei) of the fitted GP at device-resident candidates Xc[Mpad][d]
 int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const double* rep, int n_rep,
                    double tmax, int want_pei, double* mean, double* var, double* pei) {
@@ -415,6 +476,8 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
     int64_t chunk = default_chunk(gp, Mpad);
     int rc = ensure_pred_scratch(gp, chunk);
     if (rc) return rc;
+    // int8 digits bound |D_t| <= S 2^14 K < 2^31 only up to K = 16384
+    const bool use_oz = g.oz_slices > 0 && Np <= 16384;
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc_pad = std::min(chunk, Mpad - c0);
         const int64_t mc = std::min(mc_pad, M - c0);
@@ -436,6 +499,8 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
             sumsq_rows_kernel<<<(unsigned)mc, 256, 0, g.stream>>>(gp->zsmall, Np, Np, gp->P);
             prof_end(m0);
             LAUNCH_CHECK("sumsq_rows_kernel");
+        } else if (use_oz) {
+            if ((rc = variance_ozaki(gp, (int)mc_pad))) return rc;
         } else {
         GemmArgs ga{};
         ga.A = gp->fit.Linv; ga.B = gp->KcT; ga.C = gp->P;
@@ -445,7 +510,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
         if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
         }
         FinArgs f{};
-        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : Np / g.variance_bm;
+        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : (use_oz ? Np / oz::BLK_R : Np / g.variance_bm);
         f.alpha = gp->fit.alpha; f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep;
         f.N = (int)gp->N; f.Np = Np; f.d = gp->d; f.kernel_id = gp->kernel_id; f.m_valid = (int)mc;
         f.tmax = tmax; f.want_pei = want_pei;
@@ -580,6 +645,10 @@ int exq_init(int device) {
     if (const char* e = getenv("EXQ_EVAL_STREAMS")) g.eval_streams = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("EXQ_BM64_FACTOR")) g.bm64_factor = atof(e);
     if (const char* e = getenv("EXQ_VARIANCE_BM")) g.variance_bm = atoi(e) == 128 ? 128 : 64;
+    if (const char* e = getenv("EXQ_OZAKI_SLICES")) {
+        const int v = atoi(e);
+        g.oz_slices = (v >= 5 && v <= 7) ? v : 0;
+    }
     CUDA_TRY(cudaEventCreate(&g.t0));
     CUDA_TRY(cudaEventCreate(&g.t1));
     g.device = device;
@@ -594,7 +663,7 @@ int exq_shutdown(void) {
     cudaStreamSynchronize(g.stream);
     sys_pool_clear();
     if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
-    cudaFree(g.KcT); cudaFree(g.P);
+    cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes);
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
     cudaEventDestroy(g.t0);
@@ -606,6 +675,7 @@ int exq_shutdown(void) {
 }
 
 int exq_device_sm_count(void) { return g.sm_count; }
+int exq_variance_slices(void) { return g.oz_slices; }
 int64_t exq_launch_count(void) { return g.launches; }
 
 int exq_timer_start(void) {
@@ -734,6 +804,7 @@ int exq_gp_destroy(exq_gp_t gp) {
     if (!gp) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
     cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep); cudaFree(gp->zsmall);
+    cudaFree(gp->linv_planes); cudaFree(gp->linv_exp);
     sys_release(gp->fit);
     sys_release(gp->batch);
     delete gp;
@@ -748,6 +819,7 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
     int rc = sys_alloc(gp->fit, 1, (int)gp->N, d, false, false);
     if (rc) return rc;
     gp->fitted = false;
+    gp->planes_S = 0;
     std::vector<double> th(d + 2);
     for (int k = 0; k < d; k++) {
         th[k] = exp(corr_raw[k]);

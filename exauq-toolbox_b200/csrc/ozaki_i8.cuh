@@ -6,18 +6,20 @@
 // its int8 kind is exact (s32 accumulation in TMEM), so the product is rebuilt from integer
 // pieces:
 //
-//   a = 2^e_row * sum_{p=1..S} a_p 128^-p,   a_p in [-127,127]   (round-to-nearest digits)
-//   sum_k a_k b_k = 2^(e+f) * sum_{t=2..S+1} 128^-t  D_t,   D_t = sum_{p+q=t} sum_k a_p,k b_q,k
+//   a = 2^e_row * sum_{p=1..S} a_p 256^-p,   a_p in [-128,127]   (balanced base-256 digits of the
+//                                                                   value rounded to 8 S bits)
+//   sum_k a_k b_k = 2^(e+f) * sum_{t=2..S+1} 256^-t  D_t,   D_t = sum_{p+q=t} sum_k a_p,k b_q,k
 //
 // All S(S+1)/2 slice products with p+q <= S+1 are issued as tcgen05.mma.kind::i8 into S
 // accumulators (one per diagonal t) that stay in TMEM for the whole k loop; every D_t is an
-// exact integer (|D_t| < 2^29 for K <= 4096), the diagonals are combined exactly in int64 and
-// rounded to FP64 once.  S = 7 gives |error| ~ 1e-12 on the variance at N = 4096 (the FP64 path
-// itself: ~1e-14; parity target 1e-8 relative), S = 8 is at the FP64 level.
+// exact integer (|D_t| <= S 2^14 K < 2^31 for K <= 16384), the diagonals are combined exactly in
+// int64 and rounded to FP64 once.  S = 6 (48 bits, 21 products) gives |error| ~ 2e-12 on the
+// variance at N = 4096 (the FP64 path itself: ~1e-14; parity target 1e-8 relative), S = 7
+// (56 bits, 28 products) is at the FP64 level (2e-14).
 //
 // Kernel layout (one CTA per SM, persistent over (candidate tile, row block) work items):
 //   warp 0     TMA producer: per 64-byte k block one 3-D box {64 B, 128 cand, S} and one
-//              {64 B, 64 rows, S} into a 2-stage shared-memory ring (SWIZZLE_64B, K-major)
+//              {64 B, 64 rows, S} into a 2- or 3-stage shared-memory ring (SWIZZLE_64B, K-major)
 //   warp 1     single-thread tcgen05.mma issuer (UMMA 128 x 64 x 32, cta_group::1), commits to
 //              the stage's "empty" barrier and, after the last k block, to "tmem_full"
 //   warps 2-5  epilogue: tcgen05.ld of the S diagonals, exact int64 recombination, row scaling,
@@ -32,12 +34,11 @@
 namespace exq {
 namespace oz {
 
-constexpr int W = 7;            // bits per slice
+constexpr int W = 8;            // bits per slice (balanced base-256 digits)
 constexpr int BLK_C = 128;      // candidates per tile  (UMMA M, TMEM lanes)
 constexpr int BLK_R = 64;       // Linv rows per tile   (UMMA N, TMEM columns per diagonal)
 constexpr int BLK_K = 64;       // k bytes per stage (one SWIZZLE_64B row)
 constexpr int UMMA_K = 32;      // k per tcgen05.mma for 8-bit operands
-constexpr int STAGES = 2;
 constexpr int THREADS = 192;
 constexpr int RASTER_G = 8;     // candidate tiles per L2 group
 
@@ -46,21 +47,24 @@ struct Cfg {
     static constexpr int A_BYTES = S * BLK_C * BLK_K;   // candidate slices of one stage
     static constexpr int B_BYTES = S * BLK_R * BLK_K;   // Linv slices of one stage
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (227 * 1024 - 1280) / STAGE_BYTES;   // 3 for S <= 6, 2 for S = 7
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
     static constexpr int TMEM_COLS = 512;
     static_assert(S * BLK_R <= 512, "accumulators exceed TMEM");
+    static_assert(S >= 5 && S <= 7, "5 <= S <= 7 (8 S bits must fit an int64 with headroom)");
 };
 
-// exponent e with |v| * 2^-e * 128 rounding to at most 127
+// exponent e with |v| * 2^-e < 0.49: the balanced digits then represent the value without a carry
+// out of the leading digit
 __host__ __device__ inline int scale_exponent(double mx) {
     if (!(mx > 0.0)) return 0;
     int e;
 #ifdef __CUDA_ARCH__
-    e = ilogb(mx) + 1;
-    if (ldexp(mx, 7 - e) >= 127.4) e++;
+    e = ilogb(mx) + 2;
+    if (ldexp(mx, -e) >= 0.49) e++;
 #else
-    e = std::ilogb(mx) + 1;
-    if (std::ldexp(mx, 7 - e) >= 127.4) e++;
+    e = std::ilogb(mx) + 2;
+    if (std::ldexp(mx, -e) >= 0.49) e++;
 #endif
     return e;
 }
@@ -93,7 +97,9 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ s
     const int row = (int)(gid / groups_per_row);
     const int k0 = (int)(gid % groups_per_row) << 4;
     const int e = row_exp ? row_exp[row] : global_exp;
-    const double sc = pow2d(-e);
+    const double sc = pow2d(8 * S - e);
+    // adding 0x80 to every digit position turns the balanced digits into the plain bytes of x + BIAS
+    constexpr unsigned long long BIAS = 0x8080808080808080ull >> (8 * (8 - S));
     uint32_t packed[S][4];
 #pragma unroll
     for (int p = 0; p < S; p++) packed[p][0] = packed[p][1] = packed[p][2] = packed[p][3] = 0u;
@@ -107,12 +113,11 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ s
                 const int k = k0 + 2 * h + u;
                 double r = (u ? v.y : v.x) * sc;
                 if (lower && k > row) r = 0.0;
+                const unsigned long long x = (unsigned long long)__double2ll_rn(r) + BIAS;
 #pragma unroll
                 for (int p = 0; p < S; p++) {
-                    r *= 128.0;
-                    const int q = __double2int_rn(r);
-                    r -= (double)q;
-                    packed[p][(2 * h + u) >> 2] |= ((uint32_t)q & 0xffu) << (8 * ((2 * h + u) & 3));
+                    const uint32_t digit = ((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u;   // plane 0 = leading digit
+                    packed[p][(2 * h + u) >> 2] |= digit << (8 * ((2 * h + u) & 3));
                 }
             }
         }
@@ -188,7 +193,7 @@ struct Args {
     int64_t ldp;
     int n_ctile;          // candidate tiles (Mc / 128)
     int n_rblk;           // row blocks (Np / 64)
-    double out_scale;     // 2^(2 f - 70): global candidate-side scale and the diagonal weights
+    double out_scale;     // 2^(2 f - 80): global candidate-side scale and the diagonal weights
 };
 
 // work item i -> (candidate tile, row block): groups of RASTER_G candidate tiles, inside a group
@@ -208,6 +213,7 @@ template <int S>
 __global__ void __launch_bounds__(THREADS, 1)
 colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_l, Args a) {
     using C = Cfg<S>;
+    constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -317,12 +323,12 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                 }
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
-                    // diagonals u = 0..3 (weights 128^-2 .. 128^-5) and u = 4..S-1, each combined exactly
+                    // diagonals u = 0..3 (weights 256^-2 .. 256^-5) and u = 4..S-1, each combined exactly
                     int64_t hi = 0, lo = 0;
 #pragma unroll
-                    for (int u = 0; u < 4 && u < S; u++) hi = hi * 128 + (int64_t)d[u][c];
+                    for (int u = 0; u < 4 && u < S; u++) hi = hi * (1 << W) + (int64_t)d[u][c];
 #pragma unroll
-                    for (int u = 4; u < S; u++) lo = lo * 128 + (int64_t)d[u][c];
+                    for (int u = 4; u < S; u++) lo = lo * (1 << W) + (int64_t)d[u][c];
                     double z = (double)hi;
                     if (S > 4) z = fma((double)lo, LO_W, z);
                     z *= pow2d(__ldg(a.row_exp + j * BLK_R + c0 + c));
@@ -389,7 +395,7 @@ inline int launch_colsumsq(const int8_t* cand_planes, int Mc, int cand_exp, cons
     if ((rc = make_plane_map(&ml, linv_planes, Np, Np, S, BLK_R))) return rc;
     Args a{};
     a.row_exp = row_exp; a.P = P; a.ldp = ldp; a.n_ctile = Mc / BLK_C; a.n_rblk = Np / BLK_R;
-    a.out_scale = std::ldexp(1.0, 2 * cand_exp - 2 * W * 5);
+    a.out_scale = std::ldexp(1.0, 2 * cand_exp - 2 * W * 5);   // (2^f 256^-5)^2
     const int items = a.n_ctile * a.n_rblk;
     const int grid = items < sm_count ? items : sm_count;
     colsumsq_kernel<S><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(mc, ml, a);

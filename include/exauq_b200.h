@@ -51,6 +51,11 @@ int exq_init(int device);              /* select device, create stream; idempote
 int exq_shutdown(void);
 const char* exq_last_error(void);
 int exq_device_sm_count(void);
+/* Digits per operand of the int8 tensor-core variance product (csrc/ozaki_i8.cuh): 5..7 base-256
+ * digits (48 bits at the default 6), or 0 when the FP64 DMMA GEMM is used instead
+ * (EXQ_OZAKI_SLICES=0).  Either way the result is the FP64 quantity k^T K^-1 k of
+ * mogp GaussianProcess.predict (exauq/core/emulators.py:649). */
+int exq_variance_slices(void);
 /* number of kernels this library launched since process start (bench.py "gpu_launches") */
 int64_t exq_launch_count(void);
 
@@ -58,7 +63,8 @@ int64_t exq_launch_count(void);
  * region; exq_prof_* accumulates per-class kernel time between reset and get. */
 int exq_timer_start(void);
 int exq_timer_stop(double* ms);
-#define EXQ_PROF_GEMM_PREDICT 0 /* variance GEMM  Z = Linv Kc^T + column sum of squares */
+#define EXQ_PROF_GEMM_PREDICT 0 /* variance GEMM  Z = Linv Kc^T + column sum of squares; flops = FP64-equivalent
+                                   Np^2 Mc, bytes = int8 operations issued when the int8 path is active */
 #define EXQ_PROF_GEMM_FACTOR 1  /* TRSM/SYRK/TRTRI/LAUUM tile GEMMs */
 #define EXQ_PROF_LEAF 2         /* 128 x 128 potrf+trtri leaves */
 #define EXQ_PROF_ASSEMBLE 3     /* covariance assembly */

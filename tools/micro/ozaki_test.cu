@@ -93,7 +93,7 @@ int run(int Np, int Mc, int mode, int reps, const std::vector<double>& hL, const
 int main(int argc, char** argv) {
     const int Np = argc > 1 ? atoi(argv[1]) : 256, Mc = argc > 2 ? atoi(argv[2]) : 256;
     const int mode = argc > 3 ? atoi(argv[3]) : 0, reps = argc > 4 ? atoi(argv[4]) : 3;
-    const int smask = argc > 5 ? atoi(argv[5]) : 7;   // bit0: S=6, bit1: S=7, bit2: S=8
+    const int smask = argc > 5 ? atoi(argv[5]) : 7;   // bit0: S=5, bit1: S=6, bit2: S=7
     const double sigma2 = 1.7;
     std::mt19937_64 rng(1234);
     std::uniform_real_distribution<double> U(-1.0, 1.0);
@@ -154,8 +154,8 @@ int main(int argc, char** argv) {
         printf("host vs DMMA reference: max rel %.3e\n", worst);
     }
     int rc = 0;
-    if (smask & 1) rc |= run<6>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
-    if (smask & 2) rc |= run<7>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
-    if (smask & 4) rc |= run<8>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
+    if (smask & 1) rc |= run<5>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
+    if (smask & 2) rc |= run<6>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
+    if (smask & 4) rc |= run<7>(Np, Mc, mode, reps, hL, hK, sigma2, dL, dK, dPref, Pref);
     return rc;
 }
