@@ -31,6 +31,8 @@ SIGNATURES = {
     "exq_last_error": (C.c_char_p, []),
     "exq_device_sm_count": (C.c_int, []),
     "exq_variance_slices": (C.c_int, []),
+    "exq_factor_slices": (C.c_int, []),
+    "exq_set_int8_digits": (C.c_int, [C.c_int, C.c_int]),
     "exq_launch_count": (C.c_int64, []),
     "exq_timer_start": (C.c_int, []),
     "exq_timer_stop": (C.c_int, [_dp]),
@@ -329,3 +331,14 @@ def launch_count() -> int:
 def variance_slices() -> int:
     """Base-256 digits per operand of the int8 tensor-core variance product (0: FP64 DMMA GEMM)."""
     return int(load().exq_variance_slices())
+
+
+def factor_slices() -> int:
+    """Base-256 digits of the int8 GEMMs inside the factorisation (0: FP64 DMMA everywhere)."""
+    return int(load().exq_factor_slices())
+
+
+def set_int8_digits(variance_digits: int, factor_digits: int) -> None:
+    """Switch the int8 tensor-core paths at run time (0 = FP64 DMMA); applies to GPs created afterwards."""
+    init()
+    check(load().exq_set_int8_digits(int(variance_digits), int(factor_digits)), "exq_set_int8_digits")

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "leaf.cuh"
 #include "ozaki_i8.cuh"
+#include "ozaki_gemm.cuh"
 
 using namespace exq;
 
@@ -60,6 +61,10 @@ struct Ctx {
     int oz_slices = 6;
     int8_t* cand_planes = nullptr;   // [S][chunk][Np] digits of the covariance chunk
     size_t cand_planes_bytes = 0;
+    // int8 path for the large GEMMs of the potrf+trtri recursion and LAUUM (ozaki_gemm.cuh): 7 digits = 56 bits
+    // keeps the factorisation at the FP64 level (EXQ_OZAKI_FACTOR_SLICES = 0: FP64 DMMA everywhere)
+    int oz_factor_slices = 7;
+    int oz_min_k = 1024;             // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K)
 } g;
 
 int fail(int code, const std::string& msg) {
@@ -135,6 +140,8 @@ int set_kernel_attrs() {
     CUDA_TRY(oz::set_attrs<5>());
     CUDA_TRY(oz::set_attrs<6>());
     CUDA_TRY(oz::set_attrs<7>());
+    CUDA_TRY(oz::set_gemm_attrs<6>());
+    CUDA_TRY(oz::set_gemm_attrs<7>());
     const int big = 220 * 1024;
     CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -160,6 +167,9 @@ struct Sys {
     int* skip = nullptr;
     double* gpartial = nullptr;                             // gradient partials
     double* grad = nullptr;                                 // [B][d+2]
+    int8_t* oz_planes = nullptr;                            // digit planes of the int8 GEMM operands (lazy)
+    int* oz_exp = nullptr;                                  // [2][B][Np] operand row exponents
+    size_t oz_bytes = 0, oz_per_sys = 0;                    // total / per-system bytes of oz_planes
     int64_t sq() const { return (int64_t)Np * Np; }
 };
 
@@ -167,6 +177,7 @@ void sys_free(Sys& s) {
     cudaFree(s.A); cudaFree(s.Linv); cudaFree(s.W); cudaFree(s.theta); cudaFree(s.tvec);
     cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.tpart); cudaFree(s.ldq); cudaFree(s.info);
     cudaFree(s.Xb); cudaFree(s.yb); cudaFree(s.skip); cudaFree(s.gpartial); cudaFree(s.grad);
+    cudaFree(s.oz_planes); cudaFree(s.oz_exp);
     s = Sys();
 }
 
@@ -177,7 +188,7 @@ std::vector<Sys> g_sys_pool;
 const size_t SYS_POOL_LIMIT_BYTES = (size_t)48 << 30;
 
 size_t sys_bytes(const Sys& s) {
-    return (size_t)s.B * s.sq() * sizeof(double) * (s.W ? 3 : 2);
+    return (size_t)s.B * s.sq() * sizeof(double) * (s.W ? 3 : 2) + s.oz_bytes;
 }
 
 void sys_release(Sys& s) {
@@ -227,6 +238,13 @@ int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
     if (need_w) {
         int nt = s.Np / 128;
         CUDA_TRY(cudaMalloc(&s.gpartial, (size_t)B * nt * nt * (64 + 2) * sizeof(double)));
+    }
+    if (g.oz_factor_slices > 0 && s.Np >= 2 * g.oz_min_k && s.Np <= 16384) {
+        // digit planes + exponents of the int8 GEMM operands (LAUUM needs S planes of a whole matrix)
+        s.oz_per_sys = (size_t)g.oz_factor_slices * s.sq();
+        s.oz_bytes = s.oz_per_sys * B;
+        CUDA_TRY(cudaMalloc(&s.oz_planes, s.oz_bytes));
+        CUDA_TRY(cudaMalloc(&s.oz_exp, (size_t)2 * B * s.Np * sizeof(int)));
     }
     if (own_data) {
         CUDA_TRY(cudaMalloc(&s.Xb, (size_t)B * s.Np * d * sizeof(double)));
@@ -309,6 +327,59 @@ int launch_assemble(const AsmArgs& a, int rows_pad, int cols_pad, int batch) {
     return check_launch("assemble_kernel");
 }
 
+// ---- large GEMMs of the recursion on the int8 tensor cores (ozaki_gemm.cuh) --------------------
+struct OzOperand {
+    const double* p;   // sub-matrix origin inside a system (leading dimension Np, system stride Np^2)
+    int trans;         // 0: p[row][k], 1: p[k][row]
+    int mask;          // oz::MASK_*: which side of the operand's diagonal holds data
+};
+
+bool oz_gemm_wanted(const Sys& s, int M, int N, int K) {
+    return g.oz_factor_slices > 0 && K >= g.oz_min_k && K <= 16384 && (M % 128) == 0 && (N % 64) == 0 && (K % 64) == 0 &&
+           (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count && s.oz_planes &&
+           s.oz_per_sys >= (size_t)g.oz_factor_slices * s.sq() && s.oz_bytes >= s.oz_per_sys * s.B;
+}
+
+template <int S>
+int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
+              int cmode, double fl) {
+    int rc;
+    const int64_t ld = s.Np, sq = s.sq();
+    int* expA = s.oz_exp;
+    int* expB = same ? expA : s.oz_exp + (int64_t)s.B * s.Np;
+    int8_t* planesA = s.oz_planes;
+    int8_t* planesB = same ? planesA : s.oz_planes + (s.oz_per_sys / 2) * s.B;
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)s.B * K * (same ? M : M + N) * (8.0 + S));
+    oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream);
+    if (!same) oz::slice_operand<S>(Bm.p, ld, sq, N, K, s.B, Bm.trans, Bm.mask, expB, planesB, g.stream);
+    prof_end(m);
+    g.launches += same ? 1 : 3;
+    LAUNCH_CHECK("ozaki operand slicing");
+    oz::GArgs a{};
+    a.expA = expA; a.expB = expB; a.C = C; a.ldc = ld; a.strideC = sq;
+    a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
+    a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
+    m = prof_begin(EXQ_PROF_GEMM_FACTOR, fl, 0.0);
+    rc = oz::launch_gemm<S>(planesA, planesB, a, g.sm_count, g.stream);
+    prof_end(m);
+    if (rc)
+        return fail(EXQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the int8 GEMM: CUresult " + std::to_string(rc) + " M=" +
+                                      std::to_string(M) + " N=" + std::to_string(N) + " K=" + std::to_string(K) + " B=" +
+                                      std::to_string(s.B) + " planes=" + std::to_string((unsigned long long)(uintptr_t)planesA) +
+                                      "/" + std::to_string((unsigned long long)(uintptr_t)planesB));
+    return check_launch("oz::gemm_kernel");
+}
+
+int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
+            int cmode) {
+    double fl = 2.0 * M * (double)N * K * s.B;
+    if (krange != KR_FULL) fl *= 0.5;
+    if (lower_only && krange == KR_FULL) fl *= 0.5;
+    if (lower_only && krange != KR_FULL) fl *= 1.0 / 3.0;
+    if (g.oz_factor_slices == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl);
+    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl);
+}
+
 // fused recursive potrf + trtri on the diagonal block [r0, r0+n) of every system in s
 int factor_rec(Sys& s, int r0, int n) {
     const int64_t ld = s.Np, sq = s.sq();
@@ -334,19 +405,36 @@ int factor_rec(Sys& s, int r0, int n) {
     // (1) L21 := A21 * Linv11^T, parked in the Linv21 slot
     a.A = A21; a.B = Li11; a.C = Li21; a.M = n2; a.N = n1; a.K = n1;
     a.krange = KR_LE_J; a.lower_only = 0; a.cmode = C_STORE;
+    const bool oz1 = oz_gemm_wanted(s, n2, n1, n1), oz2 = oz_gemm_wanted(s, n2, n1, n2);
+    if (oz1) {
+        if ((rc = oz_gemm(s, {A21, 0, oz::MASK_NONE}, {Li11, 0, oz::MASK_LE}, false, Li21, n2, n1, n1, KR_LE_J, 0, C_STORE)))
+            return rc;
+    } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
     // (2) A22 -= L21 * L21^T (lower tiles)
     a.A = Li21; a.B = Li21; a.C = A22; a.M = n2; a.N = n2; a.K = n1;
     a.krange = KR_FULL; a.lower_only = 1; a.cmode = C_SUB;
+    if (oz_gemm_wanted(s, n2, n2, n1)) {
+        if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li21, 0, oz::MASK_NONE}, true, A22, n2, n2, n1, KR_FULL, 1, C_SUB)))
+            return rc;
+    } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
     if ((rc = factor_rec(s, r0 + n1, n2))) return rc;
     // (3) T := L21 * Linv11, parked in the (now free) A21 slot
     a.A = Li21; a.B = Li11; a.C = A21; a.M = n2; a.N = n1; a.K = n1;
     a.krange = KR_GE_J; a.lower_only = 0; a.cmode = C_STORE;
+    if (oz1) {
+        if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li11, 1, oz::MASK_GE}, false, A21, n2, n1, n1, KR_GE_J, 0, C_STORE)))
+            return rc;
+    } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
     // (4) Linv21 := -Linv22 * T
     a.A = Li22; a.B = A21; a.C = Li21; a.M = n2; a.N = n1; a.K = n2;
     a.krange = KR_LE_I; a.lower_only = 0; a.cmode = C_NEG;
+    if (oz2) {
+        if ((rc = oz_gemm(s, {Li22, 0, oz::MASK_LE}, {A21, 1, oz::MASK_NONE}, false, Li21, n2, n1, n2, KR_LE_I, 0, C_NEG)))
+            return rc;
+    } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
     return EXQ_OK;
 }
@@ -381,6 +469,8 @@ int lauum(Sys& s) {
     a.strideA = a.strideB = a.strideC = s.sq();
     a.A = s.Linv; a.B = s.Linv; a.C = s.W; a.M = a.N = a.K = s.Np;
     a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
+    if (oz_gemm_wanted(s, s.Np, s.Np, s.Np))
+        return oz_gemm(s, {s.Linv, 1, oz::MASK_GE}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np, s.Np, KR_GE_I, 1, C_STORE);
     return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
 }
 
@@ -457,7 +547,7 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
     int rc = oz::launch_colsumsq<S>(g.cand_planes, mc_pad, fexp, gp->linv_planes, gp->linv_exp, Np, gp->P, mc_pad,
                                     g.sm_count, g.stream);
     prof_end(m);
-    if (rc) return fail(EXQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the int8 variance kernel");
+    if (rc) return fail(EXQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the int8 variance kernel: CUresult " + std::to_string(rc));
     LAUNCH_CHECK("oz::colsumsq_kernel");
     return EXQ_OK;
 }
@@ -554,6 +644,11 @@ Sys sys_view(const Sys& s, int b0, int B, int dmax) {
     v.tpart += (int64_t)b0 * TRMV_T_SPLITS * 2 * s.Np;
     v.ldq += 2 * b0; v.info += b0; v.grad += (int64_t)b0 * (s.d + 2);
     if (v.gpartial) v.gpartial += (int64_t)b0 * nt * nt * (dmax + 2);
+    if (v.oz_planes) {
+        v.oz_planes += (size_t)b0 * s.oz_per_sys;
+        v.oz_exp += (int64_t)2 * b0 * s.Np;
+        v.oz_bytes = s.oz_per_sys * B;
+    }
     return v;
 }
 
@@ -645,6 +740,11 @@ int exq_init(int device) {
     if (const char* e = getenv("EXQ_EVAL_STREAMS")) g.eval_streams = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("EXQ_BM64_FACTOR")) g.bm64_factor = atof(e);
     if (const char* e = getenv("EXQ_VARIANCE_BM")) g.variance_bm = atoi(e) == 128 ? 128 : 64;
+    if (const char* e = getenv("EXQ_OZAKI_FACTOR_SLICES")) {
+        const int v = atoi(e);
+        g.oz_factor_slices = (v >= 5 && v <= 7) ? v : 0;
+    }
+    if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
     if (const char* e = getenv("EXQ_OZAKI_SLICES")) {
         const int v = atoi(e);
         g.oz_slices = (v >= 5 && v <= 7) ? v : 0;
@@ -676,6 +776,20 @@ int exq_shutdown(void) {
 
 int exq_device_sm_count(void) { return g.sm_count; }
 int exq_variance_slices(void) { return g.oz_slices; }
+int exq_factor_slices(void) { return g.oz_factor_slices; }
+int exq_set_int8_digits(int variance_digits, int factor_digits) {
+    REQUIRE_READY();
+    auto ok = [](int v) { return v == 0 || (v >= 5 && v <= 7); };
+    if (!ok(variance_digits) || !(factor_digits == 0 || factor_digits == 6 || factor_digits == 7))
+        return fail(EXQ_ERR_ARG, "exq_set_int8_digits: digits must be 0 (FP64 DMMA) or 5..7 (factorisation: 6 or 7)");
+    cudaStreamSynchronize(g.stream);
+    g.oz_slices = variance_digits;
+    if (factor_digits != g.oz_factor_slices) {
+        g.oz_factor_slices = factor_digits;
+        sys_pool_clear();   // pooled workspaces carry digit planes sized for the old setting
+    }
+    return EXQ_OK;
+}
 int64_t exq_launch_count(void) { return g.launches; }
 
 int exq_timer_start(void) {

@@ -1,0 +1,356 @@
+// General FP64-accurate tile GEMM on the int8 tcgen05 tensor cores, for the large nodes of the
+// potrf + trtri recursion and for LAUUM (K^-1 = Linv^T Linv) inside the batched log-posterior
+// evaluations (mogp GaussianProcess.logposterior / logpost_deriv as driven by
+// exauq/utilities/mogp_fitting.py:289-346).  Same digit scheme, pipeline and TMEM layout as
+// ozaki_i8.cuh; what differs is
+//   * both operands are intermediate FP64 results, so every GEMM is preceded by an exponent
+//     pass and a slicing pass over each operand (O(n^2) against the O(n^3) product); operands
+//     stored k-strided (B of the triangular-inverse merge, both operands of LAUUM) are
+//     transposed by the slicer, so the kernel only ever sees k-contiguous digit planes;
+//   * the epilogue writes FP64 tiles  C (op)= 2^(ea_i + eb_j) * sum_t 256^-t D_t.
+//
+//   C[i][j] (op)= sum_k A(i, k) * B(j, k)     i < M, j < N, k in a per-tile range (KR_*)
+#pragma once
+#include "gemm_dmma.cuh"   // KR_*, C_* enums
+#include "ozaki_i8.cuh"
+
+namespace exq {
+namespace oz {
+
+enum : int { MASK_NONE = 0, MASK_LE = 1 /* keep k <= row */, MASK_GE = 2 /* keep k >= row */ };
+
+__device__ __forceinline__ bool mask_keep(int mask, int row, int k) {
+    return mask == MASK_NONE || (mask == MASK_LE ? k <= row : k >= row);
+}
+
+// exponent of every operand row; the operand is src[row][k] (trans = 0) or src[k][row] (trans = 1)
+// one warp per row (trans = 0); for trans = 1 a 32 x 8 thread block scans 32 columns
+__global__ void __launch_bounds__(256) operand_exponent_kernel(const double* __restrict__ src, int64_t ld, int64_t stride_sys,
+                                                               int rows, int K, int trans, int mask,
+                                                               int* __restrict__ row_exp) {
+    const double* s = src + (int64_t)blockIdx.z * stride_sys;
+    int* out = row_exp + (int64_t)blockIdx.z * rows;
+    if (!trans) {
+        const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        if (row >= rows) return;
+        const int k_lo = mask == MASK_GE ? row : 0, k_hi = mask == MASK_LE ? min(row + 1, K) : K;
+        double mx = 0.0;
+        for (int k = k_lo + lane; k < k_hi; k += 32) mx = fmax(mx, fabs(s[(int64_t)row * ld + k]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) out[row] = scale_exponent(mx);
+    } else {
+        __shared__ double red[8][33];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const int row = blockIdx.x * 32 + tx;   // operand row = source column
+        double mx = 0.0;
+        if (row < rows) {
+            const int k_lo = mask == MASK_GE ? row : 0, k_hi = mask == MASK_LE ? min(row + 1, K) : K;
+            for (int k = k_lo + ty; k < k_hi; k += 8) mx = fmax(mx, fabs(s[(int64_t)k * ld + row]));
+        }
+        red[ty][tx] = mx;
+        __syncthreads();
+        if (ty == 0 && row < rows) {
+#pragma unroll
+            for (int q = 1; q < 8; q++) mx = fmax(mx, red[q][tx]);
+            out[row] = scale_exponent(mx);
+        }
+    }
+}
+
+// digits of S planes from a double scaled by 2^(8S - e)
+template <int S>
+__device__ __forceinline__ unsigned long long digits_of(double v, double sc) {
+    constexpr unsigned long long BIAS = 0x8080808080808080ull >> (8 * (8 - S));
+    return (unsigned long long)__double2ll_rn(v * sc) + BIAS;   // byte (S-1-p) ^ 0x80 = digit of plane p
+}
+
+// straight slicer for a batch of operands: out[p][b * rows + row][k]  (planes of all systems stacked)
+template <int S>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ src, int64_t ld, int64_t stride_sys,
+                                                         int rows, int K, int mask, const int* __restrict__ row_exp,
+                                                         int8_t* __restrict__ out, int64_t plane_bytes) {
+    const int groups_per_row = K >> 4;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)rows * groups_per_row) return;
+    const int b = blockIdx.z;
+    const int row = (int)(gid / groups_per_row), k0 = (int)(gid % groups_per_row) << 4;
+    const double sc = pow2d(8 * S - row_exp[(int64_t)b * rows + row]);
+    uint32_t packed[S][4];
+#pragma unroll
+    for (int p = 0; p < S; p++) packed[p][0] = packed[p][1] = packed[p][2] = packed[p][3] = 0u;
+    const bool any = mask == MASK_NONE || (mask == MASK_LE ? k0 <= row : k0 + 15 >= row);
+    if (any) {
+        const double2* s2 = reinterpret_cast<const double2*>(src + (int64_t)b * stride_sys + (int64_t)row * ld + k0);
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const double2 v = s2[h];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int k = k0 + 2 * h + u;
+                const double r = mask_keep(mask, row, k) ? (u ? v.y : v.x) : 0.0;
+                const unsigned long long x = digits_of<S>(r, sc);
+#pragma unroll
+                for (int p = 0; p < S; p++)
+                    packed[p][(2 * h + u) >> 2] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * ((2 * h + u) & 3));
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < S; p++)
+        *reinterpret_cast<uint4*>(out + p * plane_bytes + ((int64_t)b * rows + row) * K + k0) =
+            make_uint4(packed[p][0], packed[p][1], packed[p][2], packed[p][3]);
+}
+
+// transposing slicer: operand row r = source column, k = source row; 64 x 64 tiles through shared memory
+template <int S>
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ src, int64_t ld, int64_t stride_sys,
+                                                         int rows, int K, int mask, const int* __restrict__ row_exp,
+                                                         int8_t* __restrict__ out, int64_t plane_bytes) {
+    __shared__ __align__(16) uint8_t dig[S][64][64 + 16];   // [plane][operand row][k], padded against bank conflicts
+    const int b = blockIdx.z, r0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int rr = threadIdx.x & 63, kq = threadIdx.x >> 6;
+    const int row = r0 + rr;
+    // tiles entirely outside the kept triangle are all zeros
+    const bool any = mask == MASK_NONE || (mask == MASK_LE ? k0 <= r0 + 63 : k0 + 63 >= r0);
+    const double sc = pow2d(8 * S - row_exp[(int64_t)b * rows + row]);
+    const double* s = src + (int64_t)b * stride_sys;
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+        const int kk = kq + 4 * i, k = k0 + kk;
+        double v = 0.0;
+        if (any && mask_keep(mask, row, k)) v = s[(int64_t)k * ld + row];
+        const unsigned long long x = digits_of<S>(v, sc);
+#pragma unroll
+        for (int p = 0; p < S; p++) dig[p][rr][kk] = (uint8_t)(((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u);
+    }
+    __syncthreads();
+    // 64 rows x 64 bytes per plane = 256 uint4 per plane: one per thread
+    const int orow = threadIdx.x >> 2, oq = threadIdx.x & 3;
+#pragma unroll
+    for (int p = 0; p < S; p++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&dig[p][orow][oq * 16]);
+        *reinterpret_cast<uint4*>(out + p * plane_bytes + ((int64_t)b * rows + r0 + orow) * K + k0 + oq * 16) = v;
+    }
+}
+
+struct GArgs {
+    const int* expA;      // [B][M]
+    const int* expB;      // [B][N]
+    double* C;
+    int64_t ldc, strideC;
+    int M, N, K;          // multiples of 128 / 64 / 64
+    int B;
+    int krange, lower_only, cmode;
+    int heavy_last;       // tiles with larger I (or J) carry more k blocks: walk the tile list backwards
+};
+
+// k-block range [lo, hi) of output tile (I: 128 rows, J: 64 columns)
+__device__ __forceinline__ void tile_krange(int krange, int I, int J, int nkb, int& lo, int& hi) {
+    lo = 0; hi = nkb;
+    if (krange == KR_LE_J) hi = min(nkb, J + 1);
+    else if (krange == KR_GE_J) lo = J;
+    else if (krange == KR_LE_I) hi = min(nkb, 2 * I + 2);
+    else if (krange == KR_GE_I) lo = 2 * I;
+}
+// linear item -> (system, I, J); returns false for tiles skipped by lower_only
+__device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& b, int& I, int& J) {
+    const int nJ = a.N / BLK_R, nI = a.M / BLK_C;
+    b = item % a.B;
+    int t = item / a.B;
+    if (a.heavy_last) t = nI * nJ - 1 - t;
+    I = t / nJ;
+    J = t - I * nJ;
+    return !(a.lower_only && J * BLK_R > I * BLK_C + (BLK_C - 1));
+}
+
+template <int S>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GArgs a) {
+    using C = Cfg<S>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
+    const int nkb = a.K / BLK_K;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+                int b, I, J, lo, hi;
+                if (!decode_gemm_item(a, i, b, I, J)) continue;
+                tile_krange(a.krange, I, J, nkb, lo, hi);
+                for (int kb = lo; kb < hi; kb++) {
+                    mbar_wait_guard(&empty[st], ph ^ 1u);
+                    mbar_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
+                    uint8_t* sa = smem + st * C::STAGE_BYTES;
+                    tma_load_3d(sa, &map_a, kb * BLK_K, b * a.M + I * BLK_C, 0, &full[st]);
+                    tma_load_3d(sa + C::A_BYTES, &map_b, kb * BLK_K, b * a.N + J * BLK_R, 0, &full[st]);
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_i8(BLK_C, BLK_R);
+            int st = 0;
+            uint32_t ph = 0, acc_ph = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+                int b, I, J, lo, hi;
+                if (!decode_gemm_item(a, i, b, I, J)) continue;
+                tile_krange(a.krange, I, J, nkb, lo, hi);
+                mbar_wait_guard(tmem_empty, acc_ph ^ 1u);
+                tc_fence_after();
+                for (int kb = lo; kb < hi; kb++) {
+                    mbar_wait_guard(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + st * C::STAGE_BYTES);
+                    const uint64_t da0 = smem_desc_sw64(sa);
+                    const uint64_t db0 = smem_desc_sw64(sa + C::A_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
+#pragma unroll
+                        for (int p = 0; p < S; p++) {
+#pragma unroll
+                            for (int q = 0; q + p < S; q++) {
+                                const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                                const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
+                                const uint32_t accumulate = (kb > lo || ks > 0 || p > 0) ? 1u : 0u;
+                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc, accumulate);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[st]);
+                    if (kb == hi - 1) umma_commit(tmem_full);
+                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                }
+                acc_ph ^= 1u;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        uint32_t acc_ph = 0;
+        constexpr double LO_W = 1.0 / (double)(1ull << (W * (S - 4)));
+        for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+            int b, I, J;
+            if (!decode_gemm_item(a, i, b, I, J)) continue;
+            const int row = I * BLK_C + quarter * 32 + lane;
+            // 2^(ea - 40): row scale and the weight 256^-5 of the high diagonal group
+            const double row_scale = pow2d(__ldg(a.expA + (int64_t)b * a.M + row) - 2 * W * 5 / 2);
+            const int* eb = a.expB + (int64_t)b * a.N + J * BLK_R;
+            double* crow = a.C + (int64_t)b * a.strideC + (int64_t)row * a.ldc + J * BLK_R;
+            mbar_wait_guard(tmem_full, acc_ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLK_R; c0 += 16) {
+                int32_t d[S][16];
+#pragma unroll
+                for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + c0), d[u]);
+                tmem_ld_wait();
+                if (c0 + 16 == BLK_R) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
+                double z[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    int64_t hi = 0, lo = 0;
+#pragma unroll
+                    for (int u = 0; u < 4 && u < S; u++) hi = hi * (1 << W) + (int64_t)d[u][c];
+#pragma unroll
+                    for (int u = 4; u < S; u++) lo = lo * (1 << W) + (int64_t)d[u][c];
+                    double v = (double)hi;
+                    if (S > 4) v = fma((double)lo, LO_W, v);
+                    z[c] = v * row_scale * pow2d(__ldg(eb + c0 + c));
+                }
+                double2* cp = reinterpret_cast<double2*>(crow + c0);
+                if (a.cmode == C_STORE) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) cp[c] = make_double2(z[2 * c], z[2 * c + 1]);
+                } else if (a.cmode == C_NEG) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) cp[c] = make_double2(-z[2 * c], -z[2 * c + 1]);
+                } else {   // C_SUB
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        double2 o = cp[c];
+                        cp[c] = make_double2(o.x - z[2 * c], o.y - z[2 * c + 1]);
+                    }
+                }
+            }
+            acc_ph ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int S>
+inline cudaError_t set_gemm_attrs() {
+    return cudaFuncSetAttribute(gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+}
+
+// One operand of an int8 GEMM: exponents + digit planes for a batch of B matrices (rows x K each)
+template <int S>
+inline void slice_operand(const double* src, int64_t ld, int64_t stride_sys, int rows, int K, int B, int trans, int mask,
+                          int* row_exp, int8_t* planes, cudaStream_t stream) {
+    const int64_t plane_bytes = (int64_t)B * rows * K;
+    if (!trans) {
+        operand_exponent_kernel<<<dim3((rows + 7) / 8, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, 0, mask, row_exp);
+        const int64_t groups = (int64_t)rows * (K >> 4);
+        slice_rows_kernel<S><<<dim3((unsigned)((groups + 255) / 256), 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask,
+                                                                                              row_exp, planes, plane_bytes);
+    } else {
+        operand_exponent_kernel<<<dim3((rows + 31) / 32, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, 1, mask, row_exp);
+        slice_cols_kernel<S><<<dim3(rows / 64, K / 64, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
+                                                                             plane_bytes);
+    }
+}
+
+// C (op)= A B^T from digit planes: planesA [S][B*M][K], planesB [S][B*N][K]
+template <int S>
+inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs& a, int sm_count, cudaStream_t stream) {
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C))) return rc;
+    if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R))) return rc;
+    const int items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
+    const int grid = items < sm_count ? items : sm_count;
+    gemm_kernel<S><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+    return 0;
+}
+
+}  // namespace oz
+}  // namespace exq

@@ -56,6 +56,12 @@ int exq_device_sm_count(void);
  * (EXQ_OZAKI_SLICES=0).  Either way the result is the FP64 quantity k^T K^-1 k of
  * mogp GaussianProcess.predict (exauq/core/emulators.py:649). */
 int exq_variance_slices(void);
+/* Same for the large GEMMs of the potrf + trtri recursion and LAUUM inside fits and batched
+ * log-posterior evaluations (csrc/ozaki_gemm.cuh; default 7 digits = 56 bits, EXQ_OZAKI_FACTOR_SLICES). */
+int exq_factor_slices(void);
+/* Run-time switch of both (0 = FP64 DMMA).  Affects GP handles created afterwards; used by the
+ * parity tests to compare the two arithmetic paths on identical inputs. */
+int exq_set_int8_digits(int variance_digits, int factor_digits);
 /* number of kernels this library launched since process start (bench.py "gpu_launches") */
 int64_t exq_launch_count(void);
 
