@@ -65,6 +65,7 @@ struct Ctx {
     // keeps the factorisation at the FP64 level (EXQ_OZAKI_FACTOR_SLICES = 0: FP64 DMMA everywhere)
     int oz_factor_slices = 7;
     int oz_min_k = 1024;             // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K)
+    int oz_lauum_slices = 6;         // K^-1 = Linv^T Linv feeds only the gradient (parity 1e-7): 48 bits are ample
 } g;
 
 int fail(int code, const std::string& msg) {
@@ -342,24 +343,28 @@ bool oz_gemm_wanted(const Sys& s, int M, int N, int K) {
 
 template <int S>
 int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-              int cmode, double fl) {
+              int cmode, double fl, bool reuse_a) {
     int rc;
     const int64_t ld = s.Np, sq = s.sq();
     int* expA = s.oz_exp;
     int* expB = same ? expA : s.oz_exp + (int64_t)s.B * s.Np;
     int8_t* planesA = s.oz_planes;
     int8_t* planesB = same ? planesA : s.oz_planes + (s.oz_per_sys / 2) * s.B;
-    ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)s.B * K * (same ? M : M + N) * (8.0 + S));
-    oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream);
+    // reuse_a: the digit planes of A are still in place from the previous product of this node
+    ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)s.B * K * ((reuse_a ? 0 : M) + (same ? 0 : N)) * (16.0 + S));
+    if (!reuse_a) oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream);
     if (!same) oz::slice_operand<S>(Bm.p, ld, sq, N, K, s.B, Bm.trans, Bm.mask, expB, planesB, g.stream);
     prof_end(m);
-    g.launches += same ? 1 : 3;
+    g.launches += (reuse_a ? 0 : (A.trans ? 2 : 1)) + (same ? 0 : (Bm.trans ? 2 : 1)) - 1;
     LAUNCH_CHECK("ozaki operand slicing");
     oz::GArgs a{};
     a.expA = expA; a.expB = expB; a.C = C; a.ldc = ld; a.strideC = sq;
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
-    m = prof_begin(EXQ_PROF_GEMM_FACTOR, fl, 0.0);
+    {   // int8 operations issued: every (128 x 64) tile runs S(S+1)/2 products over its k range
+        const double tri = (krange != KR_FULL ? 0.5 : 1.0) * (lower_only ? (krange == KR_FULL ? 0.5 : 2.0 / 3.0) : 1.0);
+        m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, 2.0 * M * (double)N * K * s.B * tri * (S * (S + 1) / 2));
+    }
     rc = oz::launch_gemm<S>(planesA, planesB, a, g.sm_count, g.stream);
     prof_end(m);
     if (rc)
@@ -371,13 +376,14 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
 }
 
 int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-            int cmode) {
+            int cmode, bool reuse_a = false, int digits = 0) {
     double fl = 2.0 * M * (double)N * K * s.B;
     if (krange != KR_FULL) fl *= 0.5;
     if (lower_only && krange == KR_FULL) fl *= 0.5;
     if (lower_only && krange != KR_FULL) fl *= 1.0 / 3.0;
-    if (g.oz_factor_slices == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl);
-    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl);
+    if (digits == 0) digits = g.oz_factor_slices;
+    if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
+    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
 }
 
 // fused recursive potrf + trtri on the diagonal block [r0, r0+n) of every system in s
@@ -414,20 +420,23 @@ int factor_rec(Sys& s, int r0, int n) {
     // (2) A22 -= L21 * L21^T (lower tiles)
     a.A = Li21; a.B = Li21; a.C = A22; a.M = n2; a.N = n2; a.K = n1;
     a.krange = KR_FULL; a.lower_only = 1; a.cmode = C_SUB;
-    if (oz_gemm_wanted(s, n2, n2, n1)) {
+    const bool oz_syrk = oz_gemm_wanted(s, n2, n2, n1);
+    if (oz_syrk) {
         if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li21, 0, oz::MASK_NONE}, true, A22, n2, n2, n1, KR_FULL, 1, C_SUB)))
             return rc;
     } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
-    if ((rc = factor_rec(s, r0 + n1, n2))) return rc;
-    // (3) T := L21 * Linv11, parked in the (now free) A21 slot
+    // (3) T := L21 * Linv11, parked in the (now free) A21 slot.  Needs only L21 and Linv11, so it runs before the
+    // recursion on A22: the digit planes of L21 from (2) are then still in place for the int8 kernel.
     a.A = Li21; a.B = Li11; a.C = A21; a.M = n2; a.N = n1; a.K = n1;
     a.krange = KR_GE_J; a.lower_only = 0; a.cmode = C_STORE;
     if (oz1) {
-        if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li11, 1, oz::MASK_GE}, false, A21, n2, n1, n1, KR_GE_J, 0, C_STORE)))
+        if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li11, 1, oz::MASK_GE}, false, A21, n2, n1, n1, KR_GE_J, 0, C_STORE,
+                          /*reuse_a=*/oz_syrk)))
             return rc;
     } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
+    if ((rc = factor_rec(s, r0 + n1, n2))) return rc;
     // (4) Linv21 := -Linv22 * T
     a.A = Li22; a.B = A21; a.C = Li21; a.M = n2; a.N = n1; a.K = n2;
     a.krange = KR_LE_I; a.lower_only = 0; a.cmode = C_NEG;
@@ -470,7 +479,8 @@ int lauum(Sys& s) {
     a.A = s.Linv; a.B = s.Linv; a.C = s.W; a.M = a.N = a.K = s.Np;
     a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
     if (oz_gemm_wanted(s, s.Np, s.Np, s.Np))
-        return oz_gemm(s, {s.Linv, 1, oz::MASK_GE}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np, s.Np, KR_GE_I, 1, C_STORE);
+        return oz_gemm(s, {s.Linv, 1, oz::MASK_GE}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np, s.Np, KR_GE_I, 1, C_STORE,
+                       false, std::min(g.oz_lauum_slices, g.oz_factor_slices));
     return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
 }
 
@@ -520,7 +530,7 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
         cudaFree(gp->linv_planes);
         gp->linv_planes = nullptr;
         CUDA_TRY(cudaMalloc(&gp->linv_planes, (size_t)S * Np * Np));
-        ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)Np * Np * (4.0 + 0.5 * S));
+        ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)Np * Np * (8.0 + 0.5 * S));
         oz::row_exponent_lower_kernel<<<(Np + 7) / 8, 256, 0, g.stream>>>(gp->fit.Linv, Np, Np, gp->linv_exp);
         oz::launch_slice<S>(gp->fit.Linv, Np, Np, Np, gp->linv_exp, 0, 1, gp->linv_planes, g.stream);
         prof_end(m);
@@ -537,7 +547,7 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
     }
     // covariance entries lie in [0, sigma^2]: one global exponent for the candidate side
     const int fexp = oz::scale_exponent(gp->cov);
-    ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, (double)mc_pad * Np * (8.0 + S));
+    ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)mc_pad * Np * (8.0 + S));
     oz::launch_slice<S>(gp->KcT, Np, mc_pad, Np, nullptr, fexp, 0, g.cand_planes, g.stream);
     prof_end(m);
     LAUNCH_CHECK("ozaki slice candidates");
@@ -745,6 +755,7 @@ int exq_init(int device) {
         g.oz_factor_slices = (v >= 5 && v <= 7) ? v : 0;
     }
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_OZAKI_LAUUM_SLICES")) g.oz_lauum_slices = atoi(e) == 7 ? 7 : 6;
     if (const char* e = getenv("EXQ_OZAKI_SLICES")) {
         const int v = atoi(e);
         g.oz_slices = (v >= 5 && v <= 7) ? v : 0;

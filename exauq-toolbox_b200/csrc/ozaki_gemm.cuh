@@ -65,41 +65,60 @@ __device__ __forceinline__ unsigned long long digits_of(double v, double sc) {
     return (unsigned long long)__double2ll_rn(v * sc) + BIAS;   // byte (S-1-p) ^ 0x80 = digit of plane p
 }
 
-// straight slicer for a batch of operands: out[p][b * rows + row][k]  (planes of all systems stacked)
+// straight slicer for a batch of operands: out[p][b * rows + row][k]  (planes of all systems stacked).
+// One warp per row: the row maximum fixes the exponent, then the same warp re-reads the row (L1/L2
+// resident) and writes its digits, so the operand crosses HBM once.
 template <int S>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restrict__ src, int64_t ld, int64_t stride_sys,
-                                                         int rows, int K, int mask, const int* __restrict__ row_exp,
+                                                         int rows, int K, int mask, int* __restrict__ row_exp,
                                                          int8_t* __restrict__ out, int64_t plane_bytes) {
-    const int groups_per_row = K >> 4;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)rows * groups_per_row) return;
-    const int b = blockIdx.z;
-    const int row = (int)(gid / groups_per_row), k0 = (int)(gid % groups_per_row) << 4;
-    const double sc = pow2d(8 * S - row_exp[(int64_t)b * rows + row]);
-    uint32_t packed[S][4];
-#pragma unroll
-    for (int p = 0; p < S; p++) packed[p][0] = packed[p][1] = packed[p][2] = packed[p][3] = 0u;
-    const bool any = mask == MASK_NONE || (mask == MASK_LE ? k0 <= row : k0 + 15 >= row);
-    if (any) {
-        const double2* s2 = reinterpret_cast<const double2*>(src + (int64_t)b * stride_sys + (int64_t)row * ld + k0);
+    const int b = blockIdx.z, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const double* srow = src + (int64_t)b * stride_sys + (int64_t)row * ld;
+    // 16-element groups that hold kept entries
+    const int g_lo = mask == MASK_GE ? row >> 4 : 0, g_hi = mask == MASK_LE ? (row >> 4) + 1 : K >> 4;
+    double mx = 0.0;
+    for (int g = g_lo + lane; g < g_hi; g += 32) {
+        const double2* s2 = reinterpret_cast<const double2*>(srow + (g << 4));
 #pragma unroll
         for (int h = 0; h < 8; h++) {
             const double2 v = s2[h];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int k = k0 + 2 * h + u;
-                const double r = mask_keep(mask, row, k) ? (u ? v.y : v.x) : 0.0;
-                const unsigned long long x = digits_of<S>(r, sc);
-#pragma unroll
-                for (int p = 0; p < S; p++)
-                    packed[p][(2 * h + u) >> 2] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * ((2 * h + u) & 3));
-            }
+            const int k = (g << 4) + 2 * h;
+            if (mask_keep(mask, row, k)) mx = fmax(mx, fabs(v.x));
+            if (mask_keep(mask, row, k + 1)) mx = fmax(mx, fabs(v.y));
         }
     }
 #pragma unroll
-    for (int p = 0; p < S; p++)
-        *reinterpret_cast<uint4*>(out + p * plane_bytes + ((int64_t)b * rows + row) * K + k0) =
-            make_uint4(packed[p][0], packed[p][1], packed[p][2], packed[p][3]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int e = scale_exponent(mx);
+    if (lane == 0) row_exp[(int64_t)b * rows + row] = e;
+    const double sc = pow2d(8 * S - e);
+    int8_t* orow = out + ((int64_t)b * rows + row) * K;
+    for (int g = lane; g < (K >> 4); g += 32) {
+        uint32_t packed[S][4];
+#pragma unroll
+        for (int p = 0; p < S; p++) packed[p][0] = packed[p][1] = packed[p][2] = packed[p][3] = 0u;
+        if (g >= g_lo && g < g_hi) {
+            const double2* s2 = reinterpret_cast<const double2*>(srow + (g << 4));
+#pragma unroll
+            for (int h = 0; h < 8; h++) {
+                const double2 v = s2[h];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int k = (g << 4) + 2 * h + u;
+                    const double r = mask_keep(mask, row, k) ? (u ? v.y : v.x) : 0.0;
+                    const unsigned long long x = digits_of<S>(r, sc);
+#pragma unroll
+                    for (int p = 0; p < S; p++)
+                        packed[p][(2 * h + u) >> 2] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * ((2 * h + u) & 3));
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < S; p++)
+            *reinterpret_cast<uint4*>(orow + p * plane_bytes + (g << 4)) = make_uint4(packed[p][0], packed[p][1], packed[p][2], packed[p][3]);
+    }
 }
 
 // transposing slicer: operand row r = source column, k = source row; 64 x 64 tiles through shared memory
@@ -328,10 +347,8 @@ inline void slice_operand(const double* src, int64_t ld, int64_t stride_sys, int
                           int* row_exp, int8_t* planes, cudaStream_t stream) {
     const int64_t plane_bytes = (int64_t)B * rows * K;
     if (!trans) {
-        operand_exponent_kernel<<<dim3((rows + 7) / 8, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, 0, mask, row_exp);
-        const int64_t groups = (int64_t)rows * (K >> 4);
-        slice_rows_kernel<S><<<dim3((unsigned)((groups + 255) / 256), 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask,
-                                                                                              row_exp, planes, plane_bytes);
+        slice_rows_kernel<S><<<dim3((rows + 7) / 8, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
+                                                                            plane_bytes);
     } else {
         operand_exponent_kernel<<<dim3((rows + 31) / 32, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, 1, mask, row_exp);
         slice_cols_kernel<S><<<dim3(rows / 64, K / 64, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,

@@ -75,7 +75,9 @@ int exq_timer_stop(double* ms);
 #define EXQ_PROF_LEAF 2         /* 128 x 128 potrf+trtri leaves */
 #define EXQ_PROF_ASSEMBLE 3     /* covariance assembly */
 #define EXQ_PROF_STREAM 4       /* per-candidate epilogue, PEI update/argmax, vector kernels */
-#define EXQ_PROF_NCLASS 5
+#define EXQ_PROF_GEMM_FACTOR_I8 5 /* large nodes of the recursion + LAUUM on the int8 tensor cores (flops: FP64-equivalent) */
+#define EXQ_PROF_SLICE 6          /* exponent + base-256 digit passes feeding the int8 kernels (bytes moved) */
+#define EXQ_PROF_NCLASS 7
 int exq_prof_enable(int class_mask); /* bit i set: time launches of class i with event pairs */
 int exq_prof_reset(void);
 int exq_prof_get(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes);
