@@ -79,15 +79,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     // 16-element groups that hold kept entries
     const int g_lo = mask == MASK_GE ? row >> 4 : 0, g_hi = mask == MASK_LE ? (row >> 4) + 1 : K >> 4;
     double mx = 0.0;
-    for (int g = g_lo + lane; g < g_hi; g += 32) {
-        const double2* s2 = reinterpret_cast<const double2*>(srow + (g << 4));
-#pragma unroll
-        for (int h = 0; h < 8; h++) {
-            const double2 v = s2[h];
-            const int k = (g << 4) + 2 * h;
-            if (mask_keep(mask, row, k)) mx = fmax(mx, fabs(v.x));
-            if (mask_keep(mask, row, k + 1)) mx = fmax(mx, fabs(v.y));
-        }
+    for (int k0 = (g_lo << 4) + (lane << 1); k0 < (g_hi << 4); k0 += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(srow + k0);
+        if (mask_keep(mask, row, k0)) mx = fmax(mx, fabs(v.x));
+        if (mask_keep(mask, row, k0 + 1)) mx = fmax(mx, fabs(v.y));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -95,29 +90,25 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     if (lane == 0) row_exp[(int64_t)b * rows + row] = e;
     const double sc = pow2d(8 * S - e);
     int8_t* orow = out + ((int64_t)b * rows + row) * K;
-    for (int g = lane; g < (K >> 4); g += 32) {
-        uint32_t packed[S][4];
+    // 4 consecutive elements per lane: 1 KB contiguous per warp on the way in, 128 B per plane on the way out
+    for (int k0 = lane << 2; k0 < K; k0 += 128) {
+        uint32_t packed[S];
 #pragma unroll
-        for (int p = 0; p < S; p++) packed[p][0] = packed[p][1] = packed[p][2] = packed[p][3] = 0u;
-        if (g >= g_lo && g < g_hi) {
-            const double2* s2 = reinterpret_cast<const double2*>(srow + (g << 4));
+        for (int p = 0; p < S; p++) packed[p] = 0u;
+        if ((k0 >> 4) >= g_lo && (k0 >> 4) < g_hi) {
+            const double2* s2 = reinterpret_cast<const double2*>(srow + k0);
+            const double2 v0 = s2[0], v1 = s2[1];
+            const double vals[4] = {v0.x, v0.y, v1.x, v1.y};
 #pragma unroll
-            for (int h = 0; h < 8; h++) {
-                const double2 v = s2[h];
+            for (int u = 0; u < 4; u++) {
+                const double r = mask_keep(mask, row, k0 + u) ? vals[u] : 0.0;
+                const unsigned long long x = digits_of<S>(r, sc);
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int k = (g << 4) + 2 * h + u;
-                    const double r = mask_keep(mask, row, k) ? (u ? v.y : v.x) : 0.0;
-                    const unsigned long long x = digits_of<S>(r, sc);
-#pragma unroll
-                    for (int p = 0; p < S; p++)
-                        packed[p][(2 * h + u) >> 2] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * ((2 * h + u) & 3));
-                }
+                for (int p = 0; p < S; p++) packed[p] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * u);
             }
         }
 #pragma unroll
-        for (int p = 0; p < S; p++)
-            *reinterpret_cast<uint4*>(orow + p * plane_bytes + (g << 4)) = make_uint4(packed[p][0], packed[p][1], packed[p][2], packed[p][3]);
+        for (int p = 0; p < S; p++) *reinterpret_cast<uint32_t*>(orow + p * plane_bytes + k0) = packed[p];
     }
 }
 
@@ -126,7 +117,7 @@ template <int S>
 __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restrict__ src, int64_t ld, int64_t stride_sys,
                                                          int rows, int K, int mask, const int* __restrict__ row_exp,
                                                          int8_t* __restrict__ out, int64_t plane_bytes) {
-    __shared__ __align__(16) uint8_t dig[S][64][64 + 16];   // [plane][operand row][k], padded against bank conflicts
+    __shared__ uint32_t dig[S][64][17];   // [plane][operand row][4 k per word], 17-word rows: conflict-free column writes
     const int b = blockIdx.z, r0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
     const int rr = threadIdx.x & 63, kq = threadIdx.x >> 6;
     const int row = r0 + rr;
@@ -134,21 +125,30 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restric
     const bool any = mask == MASK_NONE || (mask == MASK_LE ? k0 <= r0 + 63 : k0 + 63 >= r0);
     const double sc = pow2d(8 * S - row_exp[(int64_t)b * rows + row]);
     const double* s = src + (int64_t)b * stride_sys;
-#pragma unroll 4
-    for (int i = 0; i < 16; i++) {
-        const int kk = kq + 4 * i, k = k0 + kk;
-        double v = 0.0;
-        if (any && mask_keep(mask, row, k)) v = s[(int64_t)k * ld + row];
-        const unsigned long long x = digits_of<S>(v, sc);
 #pragma unroll
-        for (int p = 0; p < S; p++) dig[p][rr][kk] = (uint8_t)(((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u);
+    for (int i = 0; i < 4; i++) {
+        const int w = kq + 4 * i;           // word = 4 consecutive k
+        uint32_t packed[S];
+#pragma unroll
+        for (int p = 0; p < S; p++) packed[p] = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = k0 + 4 * w + u;
+            double v = 0.0;
+            if (any && mask_keep(mask, row, k)) v = s[(int64_t)k * ld + row];
+            const unsigned long long x = digits_of<S>(v, sc);
+#pragma unroll
+            for (int p = 0; p < S; p++) packed[p] |= (((uint32_t)(x >> (8 * (S - 1 - p))) & 0xffu) ^ 0x80u) << (8 * u);
+        }
+#pragma unroll
+        for (int p = 0; p < S; p++) dig[p][rr][w] = packed[p];
     }
     __syncthreads();
-    // 64 rows x 64 bytes per plane = 256 uint4 per plane: one per thread
+    // 64 rows x 64 bytes per plane = 256 x 16 B per plane: one per thread
     const int orow = threadIdx.x >> 2, oq = threadIdx.x & 3;
 #pragma unroll
     for (int p = 0; p < S; p++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&dig[p][orow][oq * 16]);
+        const uint4 v = make_uint4(dig[p][orow][oq * 4], dig[p][orow][oq * 4 + 1], dig[p][orow][oq * 4 + 2], dig[p][orow][oq * 4 + 3]);
         *reinterpret_cast<uint4*>(out + p * plane_bytes + ((int64_t)b * rows + r0 + orow) * K + k0 + oq * 16) = v;
     }
 }
@@ -236,7 +236,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_i8(BLK_C, BLK_R);
             int st = 0;
             uint32_t ph = 0, acc_ph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
@@ -255,12 +254,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
 #pragma unroll
                         for (int p = 0; p < S; p++) {
+                            // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE
+                            // MMA of N = 64 m: those digit tiles are contiguous in shared memory and their
+                            // diagonals p+q .. p+q+m-1 are adjacent TMEM column blocks, so the 128-row tile is read
+                            // from shared memory once per 4 products instead of once per product (at N = 64 the
+                            // operand reads, 192 B/clk, exceed what shared memory delivers)
+                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                            const uint32_t accumulate = (kb > lo || ks > 0 || p > 0) ? 1u : 0u;
 #pragma unroll
-                            for (int q = 0; q + p < S; q++) {
-                                const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                            for (int q = 0; q + p < S; q += 4) {
+                                const int m = (S - p - q) < 4 ? (S - p - q) : 4;
                                 const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
-                                const uint32_t accumulate = (kb > lo || ks > 0 || p > 0) ? 1u : 0u;
-                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc, accumulate);
+                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
                             }
                         }
                     }

@@ -262,7 +262,6 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_i8(BLK_C, BLK_R);
             int st = 0;
             uint32_t ph = 0, acc_ph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
@@ -280,13 +279,18 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                     for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
 #pragma unroll
                         for (int p = 0; p < S; p++) {
+                            // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE
+                            // MMA of N = 64 m: those digit tiles are contiguous in shared memory and their
+                            // diagonals p+q .. p+q+m-1 are adjacent TMEM column blocks, so the 128-row tile is read
+                            // from shared memory once per 4 products instead of once per product (at N = 64 the
+                            // operand reads, 192 B/clk, exceed what shared memory delivers)
+                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                            const uint32_t accumulate = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;
 #pragma unroll
-                            for (int q = 0; q + p < S; q++) {
-                                // slices are 0-based here: diagonal index u = p + q  (t = u + 2)
-                                const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                            for (int q = 0; q + p < S; q += 4) {
+                                const int m = (S - p - q) < 4 ? (S - p - q) : 4;
                                 const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
-                                const uint32_t accumulate = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;
-                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc, accumulate);
+                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
                             }
                         }
                     }
