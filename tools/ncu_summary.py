@@ -8,7 +8,11 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg", "sm__cycles_elapsed.max",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "TPC.TriageCompute.sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg",
+        "sm__inst_executed_pipe_tmem.sum", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def metrics(rep):
@@ -47,12 +51,19 @@ def main():
              "Program: `tools/ncu_target.py` = one fit at N=4096, d=8 (124 factor GEMMs + 32 leaves), PEI over 131072",
              "candidates (4 chunks: cross assembly + variance GEMM + epilogue), a batch of 2, `logpost_batch` with R=4.",
              "Captured with `ncu --clock-control none` after the same command exited 0 without ncu.", ""]
-    for tag, fn in [("final kernels", "launches_r01_final.csv"), ("first version", "launches_r01.csv")]:
+    lines += ["Int8 tcgen05 kernels (second half of round 1): same program with `NCU_TARGET_R=15` (the bench's restart batch);",
+              "the fit and the batched evaluation run their k >= 1024 GEMMs and LAUUM as `oz::gemm_kernel`, the variance product as",
+              "`oz::colsumsq_kernel`.", ""]
+    for tag, fn in [("int8 tcgen05 kernels, R=15", "launches_r01_int8.csv"), ("final FP64 DMMA kernels, R=4", "launches_r01_final.csv"),
+                    ("first version", "launches_r01.csv")]:
         p = os.path.join(g, fn)
         if os.path.exists(p):
             lines += [f"## launch list ({tag}; `--metrics gpu__time_duration.sum`, cold-cache and serialised: compare shares)", ""]
             lines += launch_table(p) + [""]
-    reps = [("variance GEMM Z = Linv Kc^T, Np=4096, Mc=32768 -- FINAL (cp.async interleaved, fragments double-buffered across k-tiles, grouped raster)", "prof_gemm_predict_r01_final.ncu-rep"),
+    reps = [("int8 variance product oz::colsumsq_kernel<6>, Np=4096, Mc=32768 (TMA ring -> tcgen05.mma kind::i8 -> TMEM diagonals -> tcgen05.ld)", "prof_colsumsq_r01_int8.ncu-rep"),
+            ("int8 GEMMs oz::gemm_kernel<7> of the batched evaluation (R=15): node products and LAUUM", "prof_ozgemm_r01_int8.ncu-rep"),
+            ("digit slicers (straight, fused exponent pass; transposing)", "prof_slice_r01_int8.ncu-rep"),
+            ("variance GEMM Z = Linv Kc^T, Np=4096, Mc=32768 -- FINAL FP64 DMMA (cp.async interleaved, fragments double-buffered across k-tiles, grouped raster)", "prof_gemm_predict_r01_final.ncu-rep"),
             ("last three GEMM launches of logpost_batch R=4: top-level trtri merge x2 and LAUUM -- FINAL", "prof_gemm_lauum_r01_final.ncu-rep"),
             ("cross-covariance assembly, 128x64 tile, 2 CTAs/SM -- FINAL", "prof_assemble_r01_final.ncu-rep"),
             ("leaf potrf+trtri 128x128 -- FINAL", "prof_leaf_r01_final.ncu-rep"),
