@@ -17,12 +17,14 @@ for N in (512, 1024, 2048, 4096, 8192):
     st = {}
     run = lambda: design_batch(X, y, "Matern52", [0.5] * d, 1.7, 0.0, [(0.0, 1.0)] * d, cand, batch_size=16, n_tries=15, seed=12345, stats=st)
     run()
-    _lib.prof_enable(0b11); _lib.prof_reset()
+    _lib.prof_enable(0b100011); _lib.prof_reset()
     st.clear(); _lib.timer_start(); run(); ms = _lib.timer_stop()
-    pg, fg = _lib.prof_get(0), _lib.prof_get(1)
+    pg, fg, ig = _lib.prof_get(0), _lib.prof_get(1), _lib.prof_get(5)
     _lib.prof_enable(0)
     rows.append({"N": N, "design_batch_ms": ms, "candidates_per_s": M / ms * 1e3, "loo_s": st["loo_s"], "map_s": st["map_s"], "pei_s": st["pei_s"],
                  "map_evals": st["map_evals"], "variance_gemm_tflops": pg["flops"] / max(pg["ms"], 1e-9) / 1e9,
-                 "factor_gemm_tflops": fg["flops"] / max(fg["ms"], 1e-9) / 1e9})
+                 "factor_gemm_tflops": fg["flops"] / max(fg["ms"], 1e-9) / 1e9,
+                 "factor_gemm_int8_fp64_equivalent_tflops": ig["flops"] / max(ig["ms"], 1e-9) / 1e9 if ig["launches"] else None,
+                 "variance_digits": _lib.variance_slices(), "factor_digits": _lib.factor_slices()})
     print(json.dumps(rows[-1]), flush=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "size_sweep.json"), "w"), indent=1)
