@@ -409,7 +409,8 @@ def run_b200(a):
         "config": workload_config(a, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "kernels": other,
         "map_fit": {"evals_per_step_per_gpu": map_evals, "batched_rounds_per_step": map_batches},
-        "phases_s": {k: stats.get(k) for k in ("loo_s", "map_s", "map_gpu_s", "pei_s")},
+        "phases_s": {k: stats.get(k) for k in ("loo_s", "map_s", "map_gpu_s", "pei_s", "map_allgather_wait_s",
+                                                "pei_eval_call_s", "pei_argmax_s", "pei_allgather_s", "pei_add_point_s")},
         "selected_indices": [int(i) for i in out[1]],
     }
     if world == 1 and not a.no_cpu_baseline:

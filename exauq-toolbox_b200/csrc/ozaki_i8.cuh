@@ -66,7 +66,8 @@ __host__ __device__ inline int scale_exponent(double mx) {
     e = std::ilogb(mx) + 2;
     if (std::ldexp(mx, -e) >= 0.49) e++;
 #endif
-    return e;
+    // keep 2^(8S - e) and 2^(e - 40) normal numbers; rows below 2^-900 (or non-finite) degrade gracefully
+    return e < -900 ? -900 : (e > 900 ? 900 : e);
 }
 
 __device__ __forceinline__ double pow2d(int e) {   // 2^e, normal range

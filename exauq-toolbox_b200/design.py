@@ -151,7 +151,9 @@ def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats
     if done:
         k = int(np.argmin([r[0] for r in done]))
         local[0], local[1:] = done[k][0], done[k][1]
+    tg = time.perf_counter()
     gathered = comm.allgather(local)
+    stats["map_allgather_wait_s"] = time.perf_counter() - tg   # includes waiting for the slowest rank's restarts
     if not np.any(np.isfinite(gathered[:, 0])):
         raise RuntimeError("GP fitting failed")
     theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
@@ -162,13 +164,18 @@ def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats
     return gp_e, theta
 
 
-def global_argmax(cand, comm, candidate_offset: int, scale: float = 1.0):
+def global_argmax(cand, comm, candidate_offset: int, scale: float = 1.0, stats: Optional[dict] = None):
     """(value * scale, global index, point) of the best candidate over all ranks."""
+    t0 = time.perf_counter()
     i, v = cand.argmax()
     if comm.size == 1:
         return v * scale, i + candidate_offset, np.array(cand.Xc[i], dtype=float)
     msg = np.concatenate([[v * scale, float(i + candidate_offset)], cand.Xc[i]])
+    t1 = time.perf_counter()
     allm = comm.allgather(msg)
+    if stats is not None:
+        stats["pei_argmax_s"] = stats.get("pei_argmax_s", 0.0) + (t1 - t0)
+        stats["pei_allgather_s"] = stats.get("pei_allgather_s", 0.0) + (time.perf_counter() - t1)
     w = pick_global_best(allm[:, 0], allm[:, 1])
     return float(allm[w, 0]), int(allm[w, 1]), allm[w, 2:].copy()
 
@@ -244,7 +251,11 @@ def design_batch(
     # 3. PEI over this rank's candidates, batch_size rounds of arg max + repulsion update
     cand = candidates if hasattr(candidates, "pei_eval") else cand_factory(candidates)
     rep = pseudopoints(X, bounds)
+    tp = time.perf_counter()
     cand.pei_eval(gp_e, rep, float(np.max(nes)))
+    stats["pei_eval_call_s"] = time.perf_counter() - tp
+    for k in ("pei_argmax_s", "pei_allgather_s", "pei_add_point_s"):
+        stats[k] = 0.0
     pts = np.empty((batch_size, d))
     gidx = np.empty(batch_size, dtype=np.int64)
     vals = np.empty(batch_size)
@@ -255,8 +266,10 @@ def design_batch(
         gidx[:], vals[:] = li + candidate_offset, lv
     else:
         for s in range(batch_size):
-            vals[s], gidx[s], pts[s] = global_argmax(cand, comm, candidate_offset)
+            vals[s], gidx[s], pts[s] = global_argmax(cand, comm, candidate_offset, stats=stats)
+            ta = time.perf_counter()
             cand.add_point(gp_e, pts[s])
+            stats["pei_add_point_s"] += time.perf_counter() - ta
     t3 = time.perf_counter()
     stats.update(loo_s=t1 - t0, map_s=t2 - t1, pei_s=t3 - t2)
     return pts, gidx, vals, theta
