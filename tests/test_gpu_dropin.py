@@ -333,3 +333,62 @@ def test_single_level_tutorial_end_to_end(api):
     assert abs(p.estimate - g["estimate"]) < 1e-6 and abs(p.variance - g["variance"]) < 1e-6
     assert abs(p.estimate - pub["estimate"]) < 1e-6 and abs(p.variance - pub["variance"]) < 1e-6
     assert abs(p.nes_error(pub["observed"]) - pub["nes_error"]) < 1e-6
+
+
+def test_csv_in_design_points_out(api, tmp_path):
+    """The steps either side of the path, with the reference's own code:
+    simulator outputs arrive as csv files per level (TrainingDatum.read_from_csv,
+    exauq/core/modelling.py:459-532), are turned into successive-level differences with
+    create_data_for_multi_level_loo_sampling / compute_delta_coefficients
+    (exauq/core/designers.py:1381-1553), the multi-level GP is fitted on B200 GPs (hyperparameters estimated) and
+    compute_multi_level_loo_samples returns the next design point, written back as csv; the same
+    pipeline on MogpEmulators must agree."""
+    import csv
+
+    rng = np.random.default_rng(5)
+    d = 2
+    domain = api.SimulatorDomain([(0.0, 1.0)] * d)
+    X2 = rng.uniform(0.05, 0.95, (8, d))
+    X1 = np.vstack([X2, rng.uniform(0.05, 0.95, (14, d))])     # level-2 inputs are also run at level 1
+    sims = {1: lambda x: x[1] + x[0] ** 2 + x[1] ** 2 - np.sqrt(2),
+            2: lambda x: x[1] + x[0] ** 2 + x[1] ** 2 - np.sqrt(2) + 0.3 * np.sin(2 * np.pi * x[0])}
+    paths = {}
+    for lv, X in ((1, X1), (2, X2)):
+        paths[lv] = tmp_path / f"level{lv}.csv"
+        with open(paths[lv], "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["x1", "x2", "y"])
+            for x in X:
+                w.writerow([repr(float(x[0])), repr(float(x[1])), repr(float(sims[lv](x)))])
+    raw = api.MultiLevel({lv: api.TrainingDatum.read_from_csv(paths[lv], header=True) for lv in (1, 2)})
+    data = api.designers.create_data_for_multi_level_loo_sampling(raw, correlations=1)
+    coeffs = api.designers.compute_delta_coefficients(2, correlations=1)
+    assert len(data[2]) == 8 and len(data[1]) == 14          # shared inputs live at the top level only
+    outs = []
+    for make in (lambda: api.B200GaussianProcess(kernel="Matern52"), lambda: api.MogpEmulator(kernel="Matern52")):
+        mlgp = api.MultiLevelGaussianProcess([make() for _ in range(2)], coefficients=coeffs)
+        np.random.seed(77)
+        mlgp.fit(data)
+        np.random.seed(78)
+        new = api.designers.compute_multi_level_loo_samples(mlgp, domain, api.MultiLevel([1.0, 8.0]), batch_size=1,
+                                                            seeds=api.MultiLevel([5, 6]))
+        np.seterr(all="warn")
+        outs.append((mlgp, new))
+    (ours_gp, ours), (ref_gp, ref) = outs
+    for lv in (1, 2):
+        a, b = ours_gp[lv].fit_hyperparameters, ref_gp[lv].fit_hyperparameters
+        assert np.allclose(a.corr_length_scales, b.corr_length_scales, rtol=1e-3)
+        assert np.isclose(a.process_var, b.process_var, rtol=1e-3)
+    assert ours.levels == ref.levels
+    out_csv = tmp_path / "new_design_points.csv"
+    with open(out_csv, "w", newline="") as f:
+        w = csv.writer(f)
+        for lv in ours.levels:
+            for x in ours[lv]:
+                assert x in domain
+                w.writerow([lv, *np.array(x)])
+    rows = list(csv.reader(open(out_csv)))
+    assert len(rows) == sum(len(ours[lv]) for lv in ours.levels) >= 1
+    for lv in ref.levels:
+        for a, b in zip(ours[lv], ref[lv]):
+            assert np.allclose(np.array(a), np.array(b), atol=5e-3)
