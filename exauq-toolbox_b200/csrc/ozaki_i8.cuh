@@ -20,8 +20,9 @@
 // Kernel layout (one CTA per SM, persistent over (candidate tile, row block) work items):
 //   warp 0     TMA producer: per 64-byte k block one 3-D box {64 B, 128 cand, S} and one
 //              {64 B, 64 rows, S} into a 2- or 3-stage shared-memory ring (SWIZZLE_64B, K-major)
-//   warp 1     single-thread tcgen05.mma issuer (UMMA 128 x 64 x 32, cta_group::1), commits to
-//              the stage's "empty" barrier and, after the last k block, to "tmem_full"
+//   warp 1     single-thread tcgen05.mma issuer (cta_group::1, M = 128, K = 32, N = 64 m: one digit of the
+//              128-row operand against up to 4 consecutive digits of the 64-row operand per instruction),
+//              commits to the stage's "empty" barrier and, after the last k block, to "tmem_full"
 //   warps 2-5  epilogue: tcgen05.ld of the S diagonals, exact int64 recombination, row scaling,
 //              per-candidate sum of squares over the 64 rows of the block -> P[rowblock][cand]
 #pragma once
