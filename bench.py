@@ -385,6 +385,12 @@ def run_b200(a):
         add_int8(kern[fname], prof["gemm_factor_i8"], fslices)
     if vk is not None and slices:
         add_int8(vk, prof["gemm_predict"], slices)
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/ncu_summary_r01.md,
+        # Np=4096, Mc=32768, 6 digits): the 100 MB of Linv digit planes do not stay in L2 next to the streamed
+        # candidate planes, so they are re-read once per group of 8 candidate tiles; DRAM is 9 % busy, not a limiter
+        if (N, d, slices) == (4096, 8, 6):
+            vk["traffic"] = 2.577724e9 + 20.721664e6
+            vk["algorithmic_bytes"] = 6.0 * (32768 * 4096 + 4096 * 4096 / 2) + 8.0 * 64 * 32768
     elif vk is not None and (N, d) in NCU_TRAFFIC:
         vk["traffic"] = NCU_TRAFFIC[(N, d)]
         vk["algorithmic_bytes"] = 8.0 * (32768 * 4096 + 4096 * 4096 / 2)
