@@ -65,6 +65,7 @@ struct Ctx {
     // keeps the factorisation at the FP64 level (EXQ_OZAKI_FACTOR_SLICES = 0: FP64 DMMA everywhere)
     int oz_factor_slices = 7;
     int oz_min_k = 1024;             // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K)
+    int fast_corr = 1;               // branch-free exp / sqrt + compile-time kernel id in the assembly kernel (EXQ_FAST_CORR)
     int oz_lauum_slices = 6;         // K^-1 = Linv^T Linv feeds only the gradient (parity 1e-7): 48 bits are ample
 } g;
 
@@ -144,7 +145,10 @@ int set_kernel_attrs() {
     CUDA_TRY(oz::set_gemm_attrs<6>());
     CUDA_TRY(oz::set_gemm_attrs<7>());
     const int big = 220 * 1024;
-    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -323,7 +327,10 @@ int launch_assemble(const AsmArgs& a, int rows_pad, int cols_pad, int batch) {
     dim3 grid(cols_pad / ASM_BN, rows_pad / 128, batch);
     double entries = (double)rows_pad * cols_pad * batch * (a.sym ? 0.5 : 1.0);
     ProfMark m = prof_begin(EXQ_PROF_ASSEMBLE, entries * (3.0 * a.d + 30.0), entries * 8.0);
-    assemble_kernel<<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    if (!g.fast_corr) assemble_kernel<-1><<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    else if (a.kernel_id == EXQ_KERNEL_MATERN52) assemble_kernel<EXQ_KERNEL_MATERN52><<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    else if (a.kernel_id == EXQ_KERNEL_SQEXP) assemble_kernel<EXQ_KERNEL_SQEXP><<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    else assemble_kernel<EXQ_KERNEL_PRODMAT52><<<grid, ASM_THREADS, smem, g.stream>>>(a);
     prof_end(m);
     return check_launch("assemble_kernel");
 }
@@ -754,6 +761,7 @@ int exq_init(int device) {
         const int v = atoi(e);
         g.oz_factor_slices = (v >= 5 && v <= 7) ? v : 0;
     }
+    if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
     if (const char* e = getenv("EXQ_OZAKI_LAUUM_SLICES")) g.oz_lauum_slices = atoi(e) == 7 ? 7 : 6;
     if (const char* e = getenv("EXQ_OZAKI_SLICES")) {

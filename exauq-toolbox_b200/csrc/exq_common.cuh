@@ -112,6 +112,63 @@ __device__ __forceinline__ double dcorr_dr2(int kernel_id, double r2) {
     }
     return -0.5 * exp(-0.5 * r2);
 }
+// ---- branch-free FP64 exp / sqrt for the assembly and gradient kernels ------------------------
+// The library exp() / sqrt() carry slow-path branches (range checks, denormal fix-ups); with 32
+// entries per thread those branches keep the compiler from interleaving the 32 independent
+// evaluation chains, and the assembly kernel ran its FP64 pipe at 44 % (ncu).  The arguments
+// here are known: exp of a non-positive number, sqrt of a non-negative one.
+// exp(x) for x <= 0, error < 1 ulp; results below 2^-995 are returned as ~1e-300 (never compared: a
+// correlation that small multiplies a covariance into the denormal range either way)
+__device__ __forceinline__ double exp_nonpos(double x) {
+    x = fmax(x, -690.0);
+    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: rounds to an integer in the low word
+    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const int k = __double2loint(t);
+    const double kd = t - SHIFT;
+    double r = fma(kd, -6.93147180369123816490e-01, x);      // ln2 split: high part exact for |k| < 2^20
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.3888888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // p * 2^k, k >= -996
+}
+// sqrt(x) for 0 <= x, within 1 ulp; x is clamped to [1e-30, 1e30] (below: the Matern factor is 1.0 to
+// 1e-30 either way; above: exp(-sqrt(x)) is 0 either way)
+__device__ __forceinline__ double sqrt_nonneg(double x) {
+    const double xs = fmin(fmax(x, 1e-30), 1e30);
+    double y = (double)rsqrtf((float)xs);                    // 23 bits
+    const double h = 0.5 * xs;
+    y = y * fma(-h * y, y, 1.5);                             // 46 bits
+    y = y * fma(-h * y, y, 1.5);                             // > 53 bits
+    double s = xs * y;
+    return fma(fma(-s, s, xs), 0.5 * y, s);                  // final correction of s = sqrt(xs)
+}
+// corr(r2) with the kernel fixed at compile time
+template <int KID>
+__device__ __forceinline__ double corr_from_r2_t(double r2) {
+    if (KID == EXQ_KERNEL_MATERN52) {
+        const double a = sqrt_nonneg(5.0 * r2);
+        return (1.0 + a + (5.0 / 3.0) * r2) * exp_nonpos(-a);
+    }
+    return exp_nonpos(-0.5 * r2);
+}
+template <int KID>
+__device__ __forceinline__ double mat52_1d_t(double r2) {
+    const double a = sqrt_nonneg(5.0 * r2);
+    return (1.0 + a + (5.0 / 3.0) * r2) * exp_nonpos(-a);
+}
+
 // 1-D Matern-5/2 factor for the product kernel
 __device__ __forceinline__ double mat52_1d(double r2) {
     double a = sqrt(5.0 * r2);

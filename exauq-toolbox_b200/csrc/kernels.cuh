@@ -38,6 +38,9 @@ struct AsmArgs {
     int scale_sigma2;      // 0: plain correlation (no sigma2, no nugget)
 };
 
+// KID >= 0: kernel fixed at compile time + branch-free exp / sqrt (exq_common.cuh); KID = -1: the generic
+// version with the library functions and a run-time kernel id (EXQ_FAST_CORR=0, kept as the A/B reference)
+template <int KID>
 __global__ void __launch_bounds__(ASM_THREADS, EXQ_ASM_MIN_CTAS) assemble_kernel(AsmArgs p) {
     const int it = blockIdx.y, jt = blockIdx.x;
     if (p.sym && jt * ASM_BN > it * 128 + 127) return;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(ASM_THREADS, EXQ_ASM_MIN_CTAS) assemble_kernel
 
     const int ty = tid >> 4, tx = tid & 15;
     double acc[8][4];
-    const bool prod = (p.kernel_id == EXQ_KERNEL_PRODMAT52);
+    const bool prod = KID >= 0 ? (KID == EXQ_KERNEL_PRODMAT52) : (p.kernel_id == EXQ_KERNEL_PRODMAT52);
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(ASM_THREADS, EXQ_ASM_MIN_CTAS) assemble_kernel
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     double df = xi[a] - xj[b];
-                    acc[a][b] *= mat52_1d(w * df * df);
+                    acc[a][b] *= KID >= 0 ? mat52_1d_t<EXQ_KERNEL_PRODMAT52>(w * df * df) : mat52_1d(w * df * df);
                 }
         }
     }
@@ -117,7 +120,9 @@ __global__ void __launch_bounds__(ASM_THREADS, EXQ_ASM_MIN_CTAS) assemble_kernel
             const int gj = jt * ASM_BN + tx + 16 * b;
             double v;
             if (gi < p.n_i && gj < p.n_j) {
-                double cv = prod ? acc[a][b] : corr_from_r2(p.kernel_id, acc[a][b]);
+                double cv;
+                if (KID >= 0) cv = prod ? acc[a][b] : corr_from_r2_t<(KID >= 0 ? KID : 0)>(acc[a][b]);
+                else cv = prod ? acc[a][b] : corr_from_r2(p.kernel_id, acc[a][b]);
                 v = sigma2 * cv;
                 if (p.sym && gi == gj) v = sigma2 + nugget;
             } else {
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
 #pragma unroll
                 for (int k = 0; k < DMAX; k++) {
                     if (k < d) {
-                        double s5 = sqrt(5.0 * gk[k]), e = exp(-s5);
+                        double s5 = sqrt_nonneg(5.0 * gk[k]), e = exp_nonpos(-s5);
                         double mk = (1.0 + s5 + (5.0 / 3.0) * gk[k]) * e;
                         double dk = (-5.0 / 6.0) * (1.0 + s5) * e;
                         cvp *= mk;
@@ -546,11 +551,11 @@ __global__ void __launch_bounds__(256) grad_kernel(const double* __restrict__ Xa
             }
             double cv, dv;
             if (kernel_id == EXQ_KERNEL_MATERN52) {
-                double s5 = sqrt(5.0 * r2), e = exp(-s5);
+                double s5 = sqrt_nonneg(5.0 * r2), e = exp_nonpos(-s5);
                 cv = (1.0 + s5 + (5.0 / 3.0) * r2) * e;
                 dv = (-5.0 / 6.0) * (1.0 + s5) * e;
             } else {
-                cv = exp(-0.5 * r2);
+                cv = exp_nonpos(-0.5 * r2);
                 dv = -0.5 * cv;
             }
             const double f = W * sigma2 * dv;
