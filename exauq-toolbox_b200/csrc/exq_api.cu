@@ -61,6 +61,9 @@ struct Ctx {
     int oz_slices = 6;
     int8_t* cand_planes = nullptr;   // [S][chunk][Np] digits of the covariance chunk
     size_t cand_planes_bytes = 0;
+    // digit planes of Linv are per GP handle; a design batch creates and destroys a GP per step, so freed
+    // buffers are parked here (cudaMalloc / cudaFree of 100 MB synchronise the device)
+    std::vector<std::pair<size_t, int8_t*>> plane_pool;
     // int8 path for the large GEMMs of the potrf+trtri recursion and LAUUM (ozaki_gemm.cuh): 7 digits = 56 bits
     // keeps the factorisation at the FP64 level (EXQ_OZAKI_FACTOR_SLICES = 0: FP64 DMMA everywhere)
     int oz_factor_slices = 7;
@@ -274,6 +277,7 @@ struct exq_gp_s {
     double *KcT = nullptr, *P = nullptr;   // views of the global scratch
     double* zsmall = nullptr;              // [8][Np] for the small-M variance path
     int8_t* linv_planes = nullptr;         // [S][Np][Np] base-256 digits of Linv (int8 variance path), built lazily
+    size_t linv_planes_bytes = 0;
     int* linv_exp = nullptr;               // [Np] row exponents of Linv
     int planes_S = 0;                      // digits held in linv_planes (0: stale)
     int64_t chunk = 0;
@@ -527,6 +531,12 @@ int64_t default_chunk(const exq_gp_t gp, int64_t Mpad) {
     return std::min(c, Mpad);
 }
 
+void planes_park(int8_t* p, size_t bytes) {
+    if (!p) return;
+    if (g.plane_pool.size() < 4) g.plane_pool.emplace_back(bytes, p);
+    else cudaFree(p);
+}
+
 // ---- variance product on the int8 tensor cores (ozaki_i8.cuh) ---------------------------------
 template <int S>
 int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
@@ -534,9 +544,21 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
     if (gp->planes_S != S) {
         // digits of Linv: once per fit
         if (!gp->linv_exp) CUDA_TRY(cudaMalloc(&gp->linv_exp, (size_t)Np * sizeof(int)));
-        cudaFree(gp->linv_planes);
-        gp->linv_planes = nullptr;
-        CUDA_TRY(cudaMalloc(&gp->linv_planes, (size_t)S * Np * Np));
+        const size_t need_l = (size_t)S * Np * Np;
+        if (gp->linv_planes_bytes < need_l) {
+            planes_park(gp->linv_planes, gp->linv_planes_bytes);
+            gp->linv_planes = nullptr; gp->linv_planes_bytes = 0;
+            for (size_t i = 0; i < g.plane_pool.size(); i++)
+                if (g.plane_pool[i].first >= need_l && g.plane_pool[i].first <= 2 * need_l) {
+                    gp->linv_planes = g.plane_pool[i].second; gp->linv_planes_bytes = g.plane_pool[i].first;
+                    g.plane_pool.erase(g.plane_pool.begin() + i);
+                    break;
+                }
+            if (!gp->linv_planes) {
+                CUDA_TRY(cudaMalloc(&gp->linv_planes, need_l));
+                gp->linv_planes_bytes = need_l;
+            }
+        }
         ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)Np * Np * (8.0 + 0.5 * S));
         oz::row_exponent_lower_kernel<<<(Np + 7) / 8, 256, 0, g.stream>>>(gp->fit.Linv, Np, Np, gp->linv_exp);
         oz::launch_slice<S>(gp->fit.Linv, Np, Np, Np, gp->linv_exp, 0, 1, gp->linv_planes, g.stream);
@@ -783,6 +805,8 @@ int exq_shutdown(void) {
     sys_pool_clear();
     if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
     cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes);
+    for (auto& pp : g.plane_pool) cudaFree(pp.second);
+    g.plane_pool.clear();
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
     cudaEventDestroy(g.t0);
@@ -937,7 +961,8 @@ int exq_gp_destroy(exq_gp_t gp) {
     if (!gp) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
     cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep); cudaFree(gp->zsmall);
-    cudaFree(gp->linv_planes); cudaFree(gp->linv_exp);
+    planes_park(gp->linv_planes, gp->linv_planes_bytes);
+    cudaFree(gp->linv_exp);
     sys_release(gp->fit);
     sys_release(gp->batch);
     delete gp;

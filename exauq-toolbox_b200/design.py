@@ -271,7 +271,7 @@ def design_batch(
             cand.add_point(gp_e, pts[s])
             stats["pei_add_point_s"] += time.perf_counter() - ta
     t3 = time.perf_counter()
-    stats.update(loo_s=t1 - t0, map_s=t2 - t1, pei_s=t3 - t2)
+    stats.update(loo_s=t1 - t0, map_s=t2 - t1, pei_s=t3 - t2, t_end=time.perf_counter())
     return pts, gidx, vals, theta
 
 
