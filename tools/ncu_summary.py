@@ -63,6 +63,7 @@ def main():
     reps = [("int8 variance product oz::colsumsq_kernel<6>, Np=4096, Mc=32768 (TMA ring -> tcgen05.mma kind::i8 -> TMEM diagonals -> tcgen05.ld)", "prof_colsumsq_r01_int8.ncu-rep"),
             ("int8 GEMMs oz::gemm_kernel<7> of the batched evaluation (R=15): node products and LAUUM", "prof_ozgemm_r01_int8.ncu-rep"),
             ("digit slicers (straight, fused exponent pass; transposing)", "prof_slice_r01_int8.ncu-rep"),
+            ("cross-covariance assembly, compile-time kernel id + branch-free exp/sqrt -- FINAL", "prof_assemble_r01_int8.ncu-rep"),
             ("variance GEMM Z = Linv Kc^T, Np=4096, Mc=32768 -- FINAL FP64 DMMA (cp.async interleaved, fragments double-buffered across k-tiles, grouped raster)", "prof_gemm_predict_r01_final.ncu-rep"),
             ("last three GEMM launches of logpost_batch R=4: top-level trtri merge x2 and LAUUM -- FINAL", "prof_gemm_lauum_r01_final.ncu-rep"),
             ("cross-covariance assembly, 128x64 tile, 2 CTAs/SM -- FINAL", "prof_assemble_r01_final.ncu-rep"),
