@@ -282,3 +282,61 @@ def test_map_driver_lockstep_and_threaded_agree():
         if ra is not None:
             assert ra[0] == rb[0] and np.array_equal(ra[1], rb[1])
     assert s1["evals"] <= s2["evals"] and s1["batches"] >= 1
+
+
+def test_map_priors_fast_paths_are_bit_identical_to_the_scipy_formulas():
+    """priors.py evaluates the default inverse-gamma priors through vectorised expressions and a direct
+    gammaincc call; both must give exactly the doubles of the per-dimension formulas / scipy.stats.invgamma
+    they replace, otherwise the L-BFGS-B trajectories of the reference are not reproduced."""
+    import scipy.stats
+    from scipy.optimize import root
+    from scipy.stats.qmc import LatinHypercube
+
+    from exauq_toolbox_b200 import priors as P
+
+    rng = np.random.default_rng(0)
+    with np.errstate(all="ignore"):
+        for _ in range(3000):
+            a, b, x = np.exp(rng.uniform(-30, 30)), np.exp(rng.uniform(-30, 30)), 10 ** rng.uniform(-8, 2)
+            r, f = scipy.stats.invgamma.cdf(x, a, scale=b), P._invgamma_cdf(x, a, b)
+            assert r == f or (np.isnan(r) and np.isnan(f))
+        for a, b, x in [(np.inf, 1.0, 0.1), (1.0, np.inf, 0.1), (0.0, 1.0, 0.1), (1.0, 0.0, 0.1), (1.0, 1e-320, 0.1)]:
+            r, f = scipy.stats.invgamma.cdf(x, a, scale=b), P._invgamma_cdf(x, a, b)
+            assert r == f or (np.isnan(r) and np.isnan(f))
+
+    def solve_with_scipy_stats(lo, hi):
+        def resid(z):
+            a, b = np.exp(z[0]), np.exp(z[1])
+            cdf = scipy.stats.invgamma.cdf
+            return np.array([cdf(lo, a, scale=b) - 0.005, cdf(hi, a, scale=b) - 0.995])
+
+        with np.errstate(all="ignore"):
+            sol = root(resid, np.zeros(2))
+        return (float(np.exp(sol["x"][0])), float(np.exp(sol["x"][1]))) if sol["success"] else None
+
+    X = LatinHypercube(4, seed=3).random(200)
+    X[:, 2] = 0.25                                   # a degenerate dimension gets a flat prior
+    for col in X.T:
+        u = np.unique(col)
+        if u.size > 2:
+            lo, hi = float(np.median(np.diff(u))), float(u[-1] - u[0])
+            assert P._solve_invgamma(lo, hi) == solve_with_scipy_stats(lo, hi)
+    for fit_nugget in (False, True):
+        pri = P.MapPriors(X, fit_nugget=fit_nugget)
+        if fit_nugget:
+            pri.nugget = (2.5, 3e-7)                 # exercise the nugget term whatever the solver returned
+        for _ in range(2000):
+            th = rng.uniform(-4, 8, 5 + fit_nugget)
+            if fit_nugget:
+                th[5] = rng.uniform(-20, -10)
+            lengths = np.exp(-0.5 * th[:4])
+            ref = sum(pri._logp(x, prm) for x, prm in zip(lengths, pri.corr))
+            refg = np.zeros_like(th)
+            for k, (x, prm) in enumerate(zip(lengths, pri.corr)):
+                refg[k] = pri._dlogp_dx(x, prm) * (-0.5 * x)
+            if fit_nugget:
+                nu = float(np.exp(th[5]))
+                ref += pri._logp(nu, pri.nugget)
+                refg[5] = pri._dlogp_dx(nu, pri.nugget) * nu
+            assert pri.logp(th) == ref
+            assert np.array_equal(pri.dlogp_draw(th), refg)
