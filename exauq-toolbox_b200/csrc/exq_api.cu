@@ -372,6 +372,7 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.expA = expA; a.expB = expB; a.C = C; a.ldc = ld; a.strideC = sq;
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
+    a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
     {   // int8 operations issued: every (128 x 64) tile runs S(S+1)/2 products over its k range
         const double tri = (krange != KR_FULL ? 0.5 : 1.0) * (lower_only ? (krange == KR_FULL ? 0.5 : 2.0 / 3.0) : 1.0);
         m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, 2.0 * M * (double)N * K * s.B * tri * (S * (S + 1) / 2));

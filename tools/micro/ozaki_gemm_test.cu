@@ -47,6 +47,7 @@ int run_case(const Case& c, int n, int B, int ld, const std::vector<double>& hA,
     a.expA = eA; a.expB = eB; a.C = dC; a.ldc = ld; a.strideC = sq; a.M = n; a.N = n; a.K = n; a.B = B;
     a.krange = c.krange; a.lower_only = c.lower_only; a.cmode = c.cmode;
     a.heavy_last = (c.krange == KR_LE_J || c.krange == KR_LE_I) ? 1 : 0;
+    a.sys_slow = c.lower_only ? 0 : 1;
     float ms_s = 0, ms_g = 0;
     const int reps = check ? 1 : 3;
     for (int r = 0; r < reps; r++) {
