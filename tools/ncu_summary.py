@@ -87,7 +87,20 @@ def main():
             for k, v in m.items():
                 lines.append(f"- {k}: {v}")
             lines.append("")
-    lines += ["## reading", "",
+    lines += ["## reading (int8 tcgen05 kernels)", "",
+              "* `oz::colsumsq_kernel<6>`: tensor pipe 82 % active (`sm__pipe_tensor_cycles_active`, all of it the IMMA sub-pipe), L1TEX 71 %,",
+              "  L2 44 %, DRAM 9 %.  Before up to 4 digit products were grouped into one MMA of N = 64 m the same kernel showed tensor pipe 57 %,",
+              "  L1TEX 84 %: at N = 64 the shared-memory operand reads (192 B/clk) starve the pipe.  What is left is shared-memory traffic",
+              "  (TMA writes + operand reads of 128 x 64 tiles); the tile cannot grow because the S diagonal accumulators fill TMEM.",
+              "  DRAM 2.6 GB per launch against 0.87 GB of digit planes: the 100 MB of Linv planes are re-read per group of candidate tiles.",
+              "* `oz::gemm_kernel<7>` / `<6>` (captured with the systems as the FAST index of the work list): DRAM reads 5.1 GB per top-level",
+              "  launch against 0.9 GB of planes and 12.5 GB for LAUUM, DRAM 45-65 % busy, tensor pipe 66-72 %: every CTA streamed its operand",
+              "  tiles from DRAM because its neighbours worked on other systems.  With systems as the slow index the bench's time in this kernel",
+              "  went from 248 to 229 ms per step (CUDA events; the round's ncu budget was spent before a re-capture).",
+              "* slicers: the straight slicer reads its operand twice (row maximum, then digits) but the second read hits L1/L2; both are",
+              "  bandwidth-bound (L1TEX 68-88 % before the 4-elements-per-lane rewrite, which cut their time by a quarter).",
+              "* `assemble_kernel<0>`: FP64 pipe 56 % active at 2 CTAs/SM (44 % with the library exp / sqrt and a run-time kernel id).", "",
+              "## reading (FP64 DMMA kernels)", "",
               "* Variance GEMM: algorithmic bytes per launch 8*(Mc*Np + Np^2/2) = 1.14 GB.  The first 2-D raster re-read the KcT chunk once per",
               "  row tile (17.8 GB DRAM reads, L2 hit 46 %); the grouped raster (8 candidate tiles x all row tiles) brings it to ~3.3 GB (L2 hit 84 %).",
               "  DMMA pipe active 80-85 % of elapsed cycles with burst cp.async issue, ~95 % after interleaving the copies with the DMMA groups and",
