@@ -340,3 +340,32 @@ def test_map_priors_fast_paths_are_bit_identical_to_the_scipy_formulas():
                 refg[5] = pri._dlogp_dx(nu, pri.nugget) * nu
             assert pri.logp(th) == ref
             assert np.array_equal(pri.dlogp_draw(th), refg)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ carry every key the measurement contract names (so a change of
+    bench.py that drops one is caught without a GPU)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.load(open(os.path.join(root, "profiles", "bench_r01_1gpu_final.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["dtype"] == "f64" and line["data"] == "synthetic" and "workload" in line["config"]
+    assert line["gpu_launches"] > 0 and line["value"] > 0
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in line["e2e"], key
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] != line["value"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    for key in ("value", "unit", "cores", "kind", "sample"):
+        assert key in line["cpu_baseline"], key
+    for key in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert key in line["clocks"], key
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+    ref = json.load(open(os.path.join(root, "profiles", "bench_r01_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] in ("port", "reference")
