@@ -33,12 +33,15 @@ def product(A, B, S):
     """A @ B.T as the kernels compute it."""
     PA, eA, _ = digits(A, S)
     PB, eB, _ = digits(B, S)
-    D = [np.zeros((A.shape[0], B.shape[0]), dtype=np.int64) for _ in range(S)]
+    # digit products through FP64 BLAS: every partial sum is an integer below 2^53, so they are exact
+    FA, FB = PA.astype(np.float64), PB.astype(np.float64)
+    D = [np.zeros((A.shape[0], B.shape[0])) for _ in range(S)]
     for p in range(S):
         for q in range(S - p):
-            D[p + q] += PA[p] @ PB[q].T
-    for d in D:
-        assert np.max(np.abs(d)) < 2**31, "a diagonal overflows the s32 accumulator"
+            D[p + q] += FA[p] @ FB[q].T
+    for u in range(S):
+        assert np.max(np.abs(D[u])) < 2**31, "a diagonal overflows the s32 accumulator"
+        D[u] = D[u].astype(np.int64)
     hi = np.zeros_like(D[0])
     lo = np.zeros_like(D[0])
     for u in range(min(4, S)):
@@ -78,3 +81,52 @@ def test_worst_case_diagonal_fits_s32_up_to_k_16384():
     # all digits at their extreme value: |D_t| <= (t pairs) * 128 * 128 * K
     for S in (6, 7):
         assert S * 128 * 128 * 16384 < 2**31
+
+
+def test_digit_count_of_the_factorisation():
+    """Why potrf / trtri run with 7 digits: the fused potrf + trtri recursion of exq_api.cu (factor_rec), restated
+    in numpy with the int8 arithmetic for inner dimensions >= 512, on the benchmark's covariance (N = 2048 here).
+    56 bits reproduce the FP64 recursion's log-likelihood to 1e-13 and K^-1 y to a few 1e-13; with 48 bits in the
+    two triangular-inverse merges K^-1 y moves by ~1e-10 -- still inside BASELINE.json's 1e-8, but 100 x closer."""
+    import scipy.linalg as sla
+
+    from oracle import gp_oracle as orc
+    import oracle.mogp_emulator as mogp
+
+    def mm(A, Bt, S):
+        if S and A.shape[1] >= 512:
+            return product(np.ascontiguousarray(A), np.ascontiguousarray(Bt), S)
+        return A @ Bt.T
+
+    def factor(A, Li, r0, n, sp, st):
+        if n == 128:
+            L = np.linalg.cholesky(A[r0:r0 + n, r0:r0 + n])
+            A[r0:r0 + n, r0:r0 + n] = L
+            Li[r0:r0 + n, r0:r0 + n] = sla.solve_triangular(L, np.eye(n), lower=True)
+            return
+        n1 = n // 2
+        a, b, c = r0, r0 + n1, r0 + n
+        factor(A, Li, a, n1, sp, st)
+        L21 = mm(A[b:c, a:b], Li[a:b, a:b], sp)             # (1) A21 Linv11^T
+        A[b:c, b:c] -= mm(L21, L21, sp)                     # (2) SYRK
+        T = mm(L21, Li[a:b, a:b].T, st)                     # (3) L21 Linv11
+        factor(A, Li, b, n - n1, sp, st)
+        Li[b:c, a:b] = -mm(Li[b:c, b:c], T.T, st)           # (4) -Linv22 T
+        A[b:c, a:b] = L21
+
+    N, d = 2048, 8
+    X, y = orc.synthetic_problem(N, d)
+    K = 1.7 * mogp.Kernel.Matern52().kernel_f(X, X, np.full(d, -2 * np.log(0.5)))
+    out = {}
+    for name, sp, st in (("fp64", 0, 0), ("7/7", 7, 7), ("7/6", 7, 6)):
+        A, Li = K.copy(), np.zeros_like(K)
+        factor(A, Li, 0, N, sp, st)
+        t = Li @ y
+        nll = 0.5 * (2 * np.sum(np.log(np.diag(A))) + t @ t + N * np.log(2 * np.pi))
+        out[name] = (nll, Li.T @ t)
+    ref_nll, ref_alpha = out["fp64"]
+    err = {k: (abs(v[0] - ref_nll) / abs(ref_nll), np.max(np.abs(v[1] - ref_alpha)) / np.max(np.abs(ref_alpha)))
+           for k, v in out.items() if k != "fp64"}
+    assert err["7/7"][0] < 1e-13 and err["7/7"][1] < 5e-12, err
+    assert err["7/6"][0] < 1e-9 and err["7/6"][1] < 1e-8, err
+    assert err["7/6"][1] > 10 * err["7/7"][1], err
