@@ -34,6 +34,10 @@ SIGNATURES = {
     "exq_factor_slices": (C.c_int, []),
     "exq_set_int8_digits": (C.c_int, [C.c_int, C.c_int]),
     "exq_launch_count": (C.c_int64, []),
+    "exq_set_guard": (C.c_int, [C.c_double, C.c_double]),
+    "exq_guard_counts": (C.c_int, [_lp, _lp]),
+    "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
+    "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "exq_timer_start": (C.c_int, []),
     "exq_timer_stop": (C.c_int, [_dp]),
     "exq_prof_enable": (C.c_int, [C.c_int]),
@@ -188,6 +192,13 @@ class DeviceGP:
         self.nugget_used, self.logdet, self.quad = nu.value, ld.value, q.value
         return self
 
+    def kappa(self):
+        """(kappa, on_fp64): the conditioning proxy (max L_ii / min L_ii)^2 of the last fit and whether the
+        int8 guard sent that fit to the FP64 DMMA path."""
+        k, f = C.c_double(), C.c_int()
+        check(load().exq_gp_kappa(self._h, C.byref(k), C.byref(f)), "exq_gp_kappa")
+        return k.value, bool(f.value)
+
     @property
     def neg_log_likelihood(self) -> float:
         return 0.5 * (self.logdet + self.quad + self.N * np.log(2.0 * np.pi))
@@ -336,6 +347,27 @@ def variance_slices() -> int:
 def factor_slices() -> int:
     """Base-256 digits of the int8 GEMMs inside the factorisation (0: FP64 DMMA everywhere)."""
     return int(load().exq_factor_slices())
+
+
+def set_guard(widen: float = 2.0 ** 20, fallback: float = 1e12) -> None:
+    """Thresholds of the conditioning guard of the int8 paths (see include/exauq_b200.h)."""
+    init()
+    check(load().exq_set_guard(float(widen), float(fallback)), "exq_set_guard")
+
+
+def guard_counts() -> tuple[int, int]:
+    """(times a 6-digit product was widened to 7 digits, times a factorisation fell back to FP64 DMMA)."""
+    w, f = C.c_int64(), C.c_int64()
+    check(load().exq_guard_counts(C.byref(w), C.byref(f)), "exq_guard_counts")
+    return int(w.value), int(f.value)
+
+
+KR_FULL, KR_LE_J, KR_GE_J, KR_LE_I, KR_GE_I = range(5)
+
+
+def int8_gemm_ops(M: int, N: int, K: int, B: int, krange: int, lower_only: bool, digits: int) -> float:
+    """int8 operations the factorisation GEMM kernel issues for this product (host arithmetic, no GPU needed)."""
+    return float(load().exq_int8_gemm_ops(M, N, K, B, krange, int(bool(lower_only)), digits))
 
 
 def set_int8_digits(variance_digits: int, factor_digits: int) -> None:

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,14 +39,10 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // batched evaluations are split over stream + side[]
     double bm64_factor = 1e9;   // 64-row tiles (2 CTAs/SM) measured faster than 128-row tiles at every level of the
                                 // recursion (34.8 vs 36.6 ms per batched evaluation); EXQ_BM64_FACTOR=0 restores 128
     int variance_bm = 64;       // row tile of the variance GEMM (EXQ_VARIANCE_BM)
-    int eval_streams = 1;   // EXQ_EVAL_STREAMS: measured gain of 2 streams is 3 % of the MAP phase, and overlapped
-                            // kernels make per-launch event timings meaningless, so the default stays 1
     cudaEvent_t t0 = nullptr, t1 = nullptr;
-    std::string err;
     int64_t launches = 0;
     unsigned prof_mask = 0;
     std::vector<cudaEvent_t> pool;
@@ -69,11 +66,29 @@ struct Ctx {
     int oz_factor_slices = 7;
     int oz_min_k = 1024;             // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K)
     int fast_corr = 1;               // branch-free exp / sqrt + compile-time kernel id in the assembly kernel (EXQ_FAST_CORR)
-    int oz_lauum_slices = 6;         // K^-1 = Linv^T Linv feeds only the gradient (parity 1e-7): 48 bits are ample
+    int oz_lauum_slices = 6;         // K^-1 = Linv^T Linv for the gradient (parity 1e-7): 48 bits unless the guard widens
+    // ---- conditioning guard of the int8 paths ----------------------------------------------------------------
+    // kappa = (max L_ii / min L_ii)^2 is a lower bound of cond_2(K), read back with every factorisation.  The int8
+    // products round every operand row to 8 S bits relative to the row maximum, so their error relative to an
+    // FP64 product grows with the dynamic range inside the rows of L / Linv, i.e. with kappa:
+    //   kappa >= guard_widen    : 6-digit products (variance, LAUUM, kinv) are run with 7 digits (56 bits)
+    //   kappa >= guard_fallback : the factorisation itself is redone on the FP64 DMMA path and everything
+    //                             downstream (variance, LAUUM) stays on FP64 DMMA for that system
+    double guard_widen = 1048576.0;        // 2^20   (EXQ_GUARD_WIDEN)
+    double guard_fallback = 1.0e12;        //        (EXQ_GUARD_FALLBACK)
+    bool oz_off = false;                   // set while a guarded system is re-evaluated on FP64 DMMA
+    int64_t guard_widened = 0, guard_fallbacks = 0;
 } g;
 
+// Every extern "C" entry point takes this lock first: the library keeps its state (error string, scratch
+// buffers, workspace pools, the one stream) in globals, ctypes releases the GIL during calls and Python may
+// run a handle's destructor on any thread.  Recursive because entry points call each other.
+std::recursive_mutex g_api_mutex;
+#define API_LOCK() std::lock_guard<std::recursive_mutex> _api_lock(g_api_mutex)
+
+thread_local std::string g_err;   // per calling thread: exq_last_error() reports the caller's own failure
 int fail(int code, const std::string& msg) {
-    g.err = msg;
+    g_err = msg;
     return code;
 }
 
@@ -84,11 +99,10 @@ int fail(int code, const std::string& msg) {
             return fail(EXQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
     } while (0)
 
-#define REQUIRE_READY()                                                               \
-    do {                                                                              \
-        if (!g.ready) return fail(EXQ_ERR_CUDA, "exq_init has not succeeded (no GPU?)"); \
-        cudaSetDevice(g.device); /* the calling host thread may be new (per-thread current device) */ \
-    } while (0)
+#define REQUIRE_READY()                                                           \
+    API_LOCK();                                                                   \
+    if (!g.ready) return fail(EXQ_ERR_CUDA, "exq_init has not succeeded (no GPU?)"); \
+    cudaSetDevice(g.device) /* the calling host thread may be new (per-thread current device) */
 
 inline int pad128(int64_t n) { return (int)(((n + 127) / 128) * 128); }
 
@@ -169,7 +183,8 @@ struct Sys {
     double* theta = nullptr;                                // [B][d+2]
     double *tvec = nullptr, *alpha = nullptr, *dinv = nullptr, *kvec = nullptr;   // [B][Np]
     double* tpart = nullptr;                                // [B][TRMV_T_SPLITS][2][Np] partial sums
-    double* ldq = nullptr;                                  // [B][2]
+    double* ldq = nullptr;                                  // [B][2] {log det K, y^T K^-1 y}
+    double* dstat = nullptr;                                // [B][2] {min, max} of diag(L): conditioning proxy for the int8 guard
     int* info = nullptr;                                    // [B]
     double *Xb = nullptr, *yb = nullptr;                    // own data (LOO refits) or null
     int* skip = nullptr;
@@ -183,7 +198,7 @@ struct Sys {
 
 void sys_free(Sys& s) {
     cudaFree(s.A); cudaFree(s.Linv); cudaFree(s.W); cudaFree(s.theta); cudaFree(s.tvec);
-    cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.tpart); cudaFree(s.ldq); cudaFree(s.info);
+    cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.tpart); cudaFree(s.ldq); cudaFree(s.dstat); cudaFree(s.info);
     cudaFree(s.Xb); cudaFree(s.yb); cudaFree(s.skip); cudaFree(s.gpartial); cudaFree(s.grad);
     cudaFree(s.oz_planes); cudaFree(s.oz_exp);
     s = Sys();
@@ -199,8 +214,15 @@ size_t sys_bytes(const Sys& s) {
     return (size_t)s.B * s.sq() * sizeof(double) * (s.W ? 3 : 2) + s.oz_bytes;
 }
 
+// a workspace is complete when every buffer its shape calls for exists (a failed cudaMalloc leaves later ones null)
+bool sys_complete(const Sys& s) {
+    return s.A && s.Linv && s.theta && s.tvec && s.alpha && s.dinv && s.kvec && s.tpart && s.ldq && s.info && s.grad &&
+           s.dstat && (!s.W || s.gpartial) && (s.oz_bytes == 0 || (s.oz_planes && s.oz_exp)) && (!s.Xb || (s.yb && s.skip));
+}
+
 void sys_release(Sys& s) {
-    if (!s.A) { s = Sys(); return; }
+    if (!s.A) { sys_free(s); return; }
+    if (!sys_complete(s)) { sys_free(s); return; }   // never park a half-allocated workspace
     size_t held = 0;
     for (auto& q : g_sys_pool) held += sys_bytes(q);
     if (held + sys_bytes(s) <= SYS_POOL_LIMIT_BYTES && g_sys_pool.size() < 16) {
@@ -216,8 +238,51 @@ void sys_pool_clear() {
     g_sys_pool.clear();
 }
 
+void plane_pool_clear() {
+    for (auto& pp : g.plane_pool) cudaFree(pp.second);
+    g.plane_pool.clear();
+}
+
+cudaError_t sys_alloc_buffers(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
+    s.B = B; s.N = N; s.Np = pad128(N); s.d = d;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void* pp, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc((void**)pp, bytes); };
+    const size_t mat = (size_t)B * s.sq() * sizeof(double);
+    const size_t vec = (size_t)B * s.Np * sizeof(double);
+    A(&s.A, mat);
+    A(&s.Linv, mat);
+    if (need_w) A(&s.W, mat);
+    A(&s.theta, (size_t)B * (d + 2) * sizeof(double));
+    A(&s.tvec, vec);
+    A(&s.alpha, vec);
+    A(&s.dinv, vec);
+    A(&s.kvec, vec);
+    A(&s.tpart, vec * TRMV_T_SPLITS * 2);
+    A(&s.ldq, (size_t)B * 2 * sizeof(double));
+    A(&s.dstat, (size_t)B * 2 * sizeof(double));
+    A(&s.info, (size_t)B * sizeof(int));
+    A(&s.grad, (size_t)B * (d + 2) * sizeof(double));
+    if (need_w) {
+        const int nt = s.Np / 128;
+        A(&s.gpartial, (size_t)B * nt * nt * (64 + 2) * sizeof(double));
+    }
+    if (g.oz_factor_slices > 0 && s.Np >= 2 * g.oz_min_k && s.Np <= 16384) {
+        // digit planes + exponents of the int8 GEMM operands (LAUUM needs S planes of a whole matrix)
+        s.oz_per_sys = (size_t)g.oz_factor_slices * s.sq();
+        s.oz_bytes = s.oz_per_sys * B;
+        A(&s.oz_planes, s.oz_bytes);
+        A(&s.oz_exp, (size_t)2 * B * s.Np * sizeof(int));
+    }
+    if (own_data) {
+        A(&s.Xb, (size_t)B * s.Np * d * sizeof(double));
+        A(&s.yb, vec);
+        A(&s.skip, (size_t)B * sizeof(int));
+    }
+    return e;
+}
+
 int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
-    if (s.B >= B && s.N == N && s.d == d && (!need_w || s.W) && (!own_data || s.Xb)) return EXQ_OK;
+    if (s.B >= B && s.N == N && s.d == d && (!need_w || s.W) && (!own_data || s.Xb) && sys_complete(s)) return EXQ_OK;
     sys_release(s);
     for (size_t i = 0; i < g_sys_pool.size(); i++) {
         Sys& q = g_sys_pool[i];
@@ -228,36 +293,20 @@ int sys_alloc(Sys& s, int B, int N, int d, bool need_w, bool own_data) {
             return EXQ_OK;
         }
     }
-    s.B = B; s.N = N; s.Np = pad128(N); s.d = d;
-    size_t mat = (size_t)B * s.sq() * sizeof(double);
-    CUDA_TRY(cudaMalloc(&s.A, mat));
-    CUDA_TRY(cudaMalloc(&s.Linv, mat));
-    if (need_w) CUDA_TRY(cudaMalloc(&s.W, mat));
-    CUDA_TRY(cudaMalloc(&s.theta, (size_t)B * (d + 2) * sizeof(double)));
-    size_t vec = (size_t)B * s.Np * sizeof(double);
-    CUDA_TRY(cudaMalloc(&s.tvec, vec));
-    CUDA_TRY(cudaMalloc(&s.alpha, vec));
-    CUDA_TRY(cudaMalloc(&s.dinv, vec));
-    CUDA_TRY(cudaMalloc(&s.kvec, vec));
-    CUDA_TRY(cudaMalloc(&s.tpart, vec * TRMV_T_SPLITS * 2));
-    CUDA_TRY(cudaMalloc(&s.ldq, (size_t)B * 2 * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&s.info, (size_t)B * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&s.grad, (size_t)B * (d + 2) * sizeof(double)));
-    if (need_w) {
-        int nt = s.Np / 128;
-        CUDA_TRY(cudaMalloc(&s.gpartial, (size_t)B * nt * nt * (64 + 2) * sizeof(double)));
-    }
-    if (g.oz_factor_slices > 0 && s.Np >= 2 * g.oz_min_k && s.Np <= 16384) {
-        // digit planes + exponents of the int8 GEMM operands (LAUUM needs S planes of a whole matrix)
-        s.oz_per_sys = (size_t)g.oz_factor_slices * s.sq();
-        s.oz_bytes = s.oz_per_sys * B;
-        CUDA_TRY(cudaMalloc(&s.oz_planes, s.oz_bytes));
-        CUDA_TRY(cudaMalloc(&s.oz_exp, (size_t)2 * B * s.Np * sizeof(int)));
-    }
-    if (own_data) {
-        CUDA_TRY(cudaMalloc(&s.Xb, (size_t)B * s.Np * d * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&s.yb, vec));
-        CUDA_TRY(cudaMalloc(&s.skip, (size_t)B * sizeof(int)));
+    cudaError_t e = sys_alloc_buffers(s, B, N, d, need_w, own_data);
+    if (e != cudaSuccess) {
+        // out of memory: nothing partial survives; give back everything parked and try once more
+        sys_free(s);
+        cudaGetLastError();
+        sys_pool_clear();
+        plane_pool_clear();
+        e = sys_alloc_buffers(s, B, N, d, need_w, own_data);
+        if (e != cudaSuccess) {
+            sys_free(s);
+            cudaGetLastError();
+            return fail(EXQ_ERR_CUDA, std::string("workspace allocation (B=") + std::to_string(B) + ", N=" + std::to_string(N) +
+                                          "): " + cudaGetErrorString(e));
+        }
     }
     return EXQ_OK;
 }
@@ -271,11 +320,15 @@ struct exq_gp_s {
     Sys fit;                                // B = 1: fitted state
     bool fitted = false;
     double cov = 0.0, nugget = 0.0;
+    double kappa = 1.0;                     // (max L_ii / min L_ii)^2 of the fit: conditioning proxy of the int8 guard
+    bool fit_on_dmma = false;               // the guard sent this fit to the FP64 DMMA path
     std::vector<double> corr_raw;
     Sys batch;                              // MLE restarts / LOO refits
     // prediction scratch
     double *KcT = nullptr, *P = nullptr;   // views of the global scratch
     double* zsmall = nullptr;              // [8][Np] for the small-M variance path
+    double* small_x = nullptr;             // [128][d] + [2][128]: resident scratch for predict / cross_cov calls with a
+    double* small_out = nullptr;           //   handful of points (the unchanged designers call them one point at a time)
     int8_t* linv_planes = nullptr;         // [S][Np][Np] base-256 digits of Linv (int8 variance path), built lazily
     size_t linv_planes_bytes = 0;
     int* linv_exp = nullptr;               // [Np] row exponents of Linv
@@ -346,10 +399,24 @@ struct OzOperand {
     int mask;          // oz::MASK_*: which side of the operand's diagonal holds data
 };
 
-bool oz_gemm_wanted(const Sys& s, int M, int N, int K) {
-    return g.oz_factor_slices > 0 && K >= g.oz_min_k && K <= 16384 && (M % 128) == 0 && (N % 64) == 0 && (K % 64) == 0 &&
-           (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count && s.oz_planes &&
-           s.oz_per_sys >= (size_t)g.oz_factor_slices * s.sq() && s.oz_bytes >= s.oz_per_sys * s.B;
+// digit planes of both operands (A in the first half of the per-system workspace, B in the second; one operand
+// when A == B) must fit what sys_alloc sized for oz_factor_slices digits of one whole matrix
+bool oz_planes_fit(const Sys& s, int digits, int M, int N, int K, bool same) {
+    if (!s.oz_planes || s.oz_bytes < s.oz_per_sys * s.B) return false;
+    if (same) return (size_t)digits * M * K <= s.oz_per_sys;
+    return (size_t)digits * M * K <= s.oz_per_sys / 2 && (size_t)digits * N * K <= s.oz_per_sys / 2;
+}
+
+bool oz_gemm_wanted(const Sys& s, int M, int N, int K, bool same = false) {
+    return !g.oz_off && (g.oz_factor_slices == 6 || g.oz_factor_slices == 7) && K >= g.oz_min_k && K <= 16384 &&
+           (M % 128) == 0 && (N % 64) == 0 && (K % 64) == 0 && (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count &&
+           oz_planes_fit(s, g.oz_factor_slices, M, N, K, same);
+}
+
+// does the recursion over this workspace send any product to the int8 kernel?  (the top node has the largest ones)
+bool factor_uses_int8(const Sys& s) {
+    const int nb = s.Np / 128, n1 = ((nb + 1) / 2) * 128, n2 = s.Np - n1;
+    return n2 > 0 && (oz_gemm_wanted(s, n2, n1, n1) || oz_gemm_wanted(s, n2, n2, n1, true) || oz_gemm_wanted(s, n2, n1, n2));
 }
 
 template <int S>
@@ -373,10 +440,9 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
     a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
-    {   // int8 operations issued: every (128 x 64) tile runs S(S+1)/2 products over its k range
-        const double tri = (krange != KR_FULL ? 0.5 : 1.0) * (lower_only ? (krange == KR_FULL ? 0.5 : 2.0 / 3.0) : 1.0);
-        m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, 2.0 * M * (double)N * K * s.B * tri * (S * (S + 1) / 2));
-    }
+    // int8 operations issued: every non-skipped (128 x 64) tile runs S(S+1)/2 digit products over its k range --
+    // counted by the same tile walk the kernel does (round 1 counted LAUUM twice: 2/3 instead of 1/3 of the cube)
+    m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, oz::gemm_issued_ops(M, N, K, s.B, krange, lower_only, S));
     rc = oz::launch_gemm<S>(planesA, planesB, a, g.sm_count, g.stream);
     prof_end(m);
     if (rc)
@@ -394,6 +460,9 @@ int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int 
     if (lower_only && krange == KR_FULL) fl *= 0.5;
     if (lower_only && krange != KR_FULL) fl *= 1.0 / 3.0;
     if (digits == 0) digits = g.oz_factor_slices;
+    if ((digits != 6 && digits != 7) || !oz_planes_fit(s, digits, M, N, K, same))
+        return fail(EXQ_ERR_STATE, "int8 GEMM: " + std::to_string(digits) + " digits of a " + std::to_string(M) + " x " +
+                                       std::to_string(K) + " operand do not fit the digit-plane workspace");
     if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
     return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
 }
@@ -432,7 +501,7 @@ int factor_rec(Sys& s, int r0, int n) {
     // (2) A22 -= L21 * L21^T (lower tiles)
     a.A = Li21; a.B = Li21; a.C = A22; a.M = n2; a.N = n2; a.K = n1;
     a.krange = KR_FULL; a.lower_only = 1; a.cmode = C_SUB;
-    const bool oz_syrk = oz_gemm_wanted(s, n2, n2, n1);
+    const bool oz_syrk = oz_gemm_wanted(s, n2, n2, n1, true);
     if (oz_syrk) {
         if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li21, 0, oz::MASK_NONE}, true, A22, n2, n2, n1, KR_FULL, 1, C_SUB)))
             return rc;
@@ -477,22 +546,22 @@ int solve_vectors(Sys& s, const double* y, int64_t strideY, int nvalid) {
     prof_end(m);
     LAUNCH_CHECK("trmv_t_reduce_kernel");
     m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
-    logdet_quad_kernel<<<s.B, 256, 0, g.stream>>>(s.A, ld, sq, y, strideY, s.alpha, s.Np, nvalid, s.ldq);
+    logdet_quad_kernel<<<s.B, 256, 0, g.stream>>>(s.A, ld, sq, y, strideY, s.alpha, s.Np, nvalid, s.ldq, s.dstat);
     prof_end(m);
     LAUNCH_CHECK("logdet_quad_kernel");
     return EXQ_OK;
 }
 
-// K^-1 (lower tiles) into s.W
-int lauum(Sys& s) {
+// K^-1 (lower tiles) into s.W; digits: base-256 digits of the int8 product (0: the configured LAUUM digits)
+int lauum(Sys& s, int digits = 0) {
     GemmArgs a{};
     a.lda = a.ldb = a.ldc = s.Np;
     a.strideA = a.strideB = a.strideC = s.sq();
     a.A = s.Linv; a.B = s.Linv; a.C = s.W; a.M = a.N = a.K = s.Np;
     a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
-    if (oz_gemm_wanted(s, s.Np, s.Np, s.Np))
+    if (oz_gemm_wanted(s, s.Np, s.Np, s.Np, true))
         return oz_gemm(s, {s.Linv, 1, oz::MASK_GE}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np, s.Np, KR_GE_I, 1, C_STORE,
-                       false, std::min(g.oz_lauum_slices, g.oz_factor_slices));
+                       false, digits ? std::min(digits, g.oz_factor_slices) : std::min(g.oz_lauum_slices, g.oz_factor_slices));
     return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
 }
 
@@ -521,6 +590,12 @@ int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
     gp->KcT = g.KcT;
     gp->P = g.P;
     gp->chunk = want_chunk;
+    return EXQ_OK;
+}
+
+int ensure_small_scratch(exq_gp_t gp) {
+    if (!gp->small_x) CUDA_TRY(cudaMalloc(&gp->small_x, (size_t)128 * gp->d * sizeof(double)));
+    if (!gp->small_out) CUDA_TRY(cudaMalloc(&gp->small_out, (size_t)2 * 128 * sizeof(double)));
     return EXQ_OK;
 }
 
@@ -591,8 +666,15 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
     LAUNCH_CHECK("oz::colsumsq_kernel");
     return EXQ_OK;
 }
-int variance_ozaki(exq_gp_t gp, int mc_pad) {
-    switch (g.oz_slices) {
+// digits of the variance product for this GP: the configured count, widened to 7 by the conditioning guard;
+// 0 = FP64 DMMA GEMM (int8 switched off, K beyond the exact-accumulation bound, or the guard's fallback)
+int variance_digits(const exq_gp_t gp) {
+    if (g.oz_slices <= 0 || gp->Np > 16384 || gp->fit_on_dmma || gp->kappa >= g.guard_fallback) return 0;
+    if (g.oz_slices < 7 && gp->kappa >= g.guard_widen) return 7;
+    return g.oz_slices;
+}
+int variance_ozaki(exq_gp_t gp, int mc_pad, int digits) {
+    switch (digits) {
         case 5: return variance_ozaki_s<5>(gp, mc_pad);
         case 7: return variance_ozaki_s<7>(gp, mc_pad);
         default: return variance_ozaki_s<6>(gp, mc_pad);
@@ -607,7 +689,9 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
     int rc = ensure_pred_scratch(gp, chunk);
     if (rc) return rc;
     // int8 digits bound |D_t| <= S 2^14 K < 2^31 only up to K = 16384
-    const bool use_oz = g.oz_slices > 0 && Np <= 16384;
+    const int vdigits = variance_digits(gp);
+    const bool use_oz = vdigits > 0;
+    if (use_oz && vdigits != g.oz_slices && Mpad > 8) g.guard_widened++;
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc_pad = std::min(chunk, Mpad - c0);
         const int64_t mc = std::min(mc_pad, M - c0);
@@ -630,7 +714,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
             prof_end(m0);
             LAUNCH_CHECK("sumsq_rows_kernel");
         } else if (use_oz) {
-            if ((rc = variance_ozaki(gp, (int)mc_pad))) return rc;
+            if ((rc = variance_ozaki(gp, (int)mc_pad, vdigits))) return rc;
         } else {
         GemmArgs ga{};
         ga.A = gp->fit.Linv; ga.B = gp->KcT; ga.C = gp->P;
@@ -682,7 +766,7 @@ Sys sys_view(const Sys& s, int b0, int B, int dmax) {
     v.theta += (int64_t)b0 * (s.d + 2);
     v.tvec += (int64_t)b0 * s.Np; v.alpha += (int64_t)b0 * s.Np; v.dinv += (int64_t)b0 * s.Np; v.kvec += (int64_t)b0 * s.Np;
     v.tpart += (int64_t)b0 * TRMV_T_SPLITS * 2 * s.Np;
-    v.ldq += 2 * b0; v.info += b0; v.grad += (int64_t)b0 * (s.d + 2);
+    v.ldq += 2 * b0; v.dstat += 2 * b0; v.info += b0; v.grad += (int64_t)b0 * (s.d + 2);
     if (v.gpartial) v.gpartial += (int64_t)b0 * nt * nt * (dmax + 2);
     if (v.oz_planes) {
         v.oz_planes += (size_t)b0 * s.oz_per_sys;
@@ -692,18 +776,23 @@ Sys sys_view(const Sys& s, int b0, int B, int dmax) {
     return v;
 }
 
-// enqueue (no host synchronisation) one full evaluation of the systems in s on the current stream:
-// assembly, potrf+trtri, alpha / diag K^-1 / logdet / quad and, if want_grad, LAUUM + gradient
-int enqueue_logpost(exq_gp_t gp, Sys& s, const double* theta_host, bool want_grad, int dmax) {
-    const int N = (int)gp->N, d = gp->d, Np = gp->Np, nt = Np / 128, B = s.B;
+// enqueue (no host synchronisation) the first half of an evaluation of the systems in s: assembly, potrf+trtri,
+// alpha / diag K^-1 / logdet / quad / diag(L) range
+int enqueue_factor(exq_gp_t gp, Sys& s, const double* theta_host) {
+    const int N = (int)gp->N, d = gp->d, B = s.B;
     int rc;
     CUDA_TRY(cudaMemcpyAsync(s.theta, theta_host, (size_t)B * (d + 2) * sizeof(double), cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaMemsetAsync(s.info, 0, B * sizeof(int), g.stream));
     if ((rc = assemble_sym(s, gp->X, 0, N, gp->kernel_id))) return rc;
     if ((rc = factor_rec(s, 0, s.Np))) return rc;
-    if ((rc = solve_vectors(s, gp->y, 0, N))) return rc;
-    if (!want_grad) return EXQ_OK;
-    if ((rc = lauum(s))) return rc;
+    return solve_vectors(s, gp->y, 0, N);
+}
+
+// second half: K^-1 = Linv^T Linv (LAUUM) and the gradient contraction
+int enqueue_grad(exq_gp_t gp, Sys& s, int dmax, int lauum_digits) {
+    const int N = (int)gp->N, d = gp->d, Np = gp->Np, nt = Np / 128, B = s.B;
+    int rc;
+    if ((rc = lauum(s, lauum_digits))) return rc;
     size_t smem = ((size_t)128 * d + (size_t)d * GRAD_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
     dim3 grid(nt, nt, B);
     ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)B * N * N * 0.5 * (5.0 * d + 40.0), (double)B * N * N * 4.0);
@@ -749,6 +838,27 @@ void cand_free_buffers(exq_cand_s* c) {
     cudaFree(c->partial); cudaFree(c->best); cudaFree(c->chosen); cudaFree(c->xnew);
 }
 
+// lambda_max of a symmetric positive definite operator by power iteration; apply(x -> y) enqueues y = Op x
+template <class Apply>
+int power_iteration(Apply apply, double* x, double* y, double* norm_dev, int n, int nvalid, int iters, double* lambda) {
+    // positive, non-constant start vector on the real rows, zero on the padding (which the operators keep at zero)
+    std::vector<double> ones(n, 0.0);
+    for (int i = 0; i < nvalid; i++) ones[i] = 1.0 + 0.37 * ((i * 2654435761u) % 1024) / 1024.0;
+    CUDA_TRY(cudaMemcpyAsync(x, ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    normalize_kernel<<<1, 256, 0, g.stream>>>(x, n, norm_dev);
+    for (int it = 0; it < iters; it++) {
+        int rc = apply(x, y);
+        if (rc) return rc;
+        normalize_kernel<<<1, 256, 0, g.stream>>>(y, n, norm_dev);   // |Op x| with |x| = 1 -> lambda_max from below
+        std::swap(x, y);
+    }
+    g.launches += 1 + iters;
+    LAUNCH_CHECK("power iteration");
+    CUDA_TRY(cudaMemcpyAsync(lambda, norm_dev, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return EXQ_OK;
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -756,9 +866,10 @@ void cand_free_buffers(exq_cand_s* c) {
 // =====================================================================================
 extern "C" {
 
-const char* exq_last_error(void) { return g.err.c_str(); }
+const char* exq_last_error(void) { return g_err.c_str(); }
 
 int exq_init(int device) {
+    API_LOCK();
     if (g.ready && g.device == device) return EXQ_OK;
     if (g.ready) return fail(EXQ_ERR_STATE, "already initialised on another device");
     int n = 0;
@@ -776,16 +887,16 @@ int exq_init(int device) {
                                       std::to_string(prop.major) + std::to_string(prop.minor));
     g.sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    for (auto& st : g.side) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    if (const char* e = getenv("EXQ_EVAL_STREAMS")) g.eval_streams = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("EXQ_BM64_FACTOR")) g.bm64_factor = atof(e);
     if (const char* e = getenv("EXQ_VARIANCE_BM")) g.variance_bm = atoi(e) == 128 ? 128 : 64;
     if (const char* e = getenv("EXQ_OZAKI_FACTOR_SLICES")) {
         const int v = atoi(e);
-        g.oz_factor_slices = (v >= 5 && v <= 7) ? v : 0;
+        g.oz_factor_slices = (v == 6 || v == 7) ? v : 0;   // only S = 6 and 7 are instantiated (as exq_set_int8_digits)
     }
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_GUARD_WIDEN")) g.guard_widen = std::max(1.0, atof(e));
+    if (const char* e = getenv("EXQ_GUARD_FALLBACK")) g.guard_fallback = std::max(g.guard_widen, atof(e));
     if (const char* e = getenv("EXQ_OZAKI_LAUUM_SLICES")) g.oz_lauum_slices = atoi(e) == 7 ? 7 : 6;
     if (const char* e = getenv("EXQ_OZAKI_SLICES")) {
         const int v = atoi(e);
@@ -801,18 +912,17 @@ int exq_init(int device) {
 }
 
 int exq_shutdown(void) {
+    API_LOCK();
     if (!g.ready) return EXQ_OK;
     cudaStreamSynchronize(g.stream);
     sys_pool_clear();
     if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
     cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes);
-    for (auto& pp : g.plane_pool) cudaFree(pp.second);
-    g.plane_pool.clear();
+    plane_pool_clear();
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
     cudaEventDestroy(g.t0);
     cudaEventDestroy(g.t1);
-    for (auto st : g.side) cudaStreamDestroy(st);
     cudaStreamDestroy(g.stream);
     g = Ctx();
     return EXQ_OK;
@@ -835,6 +945,33 @@ int exq_set_int8_digits(int variance_digits, int factor_digits) {
     return EXQ_OK;
 }
 int64_t exq_launch_count(void) { return g.launches; }
+
+int exq_set_guard(double widen, double fallback) {
+    REQUIRE_READY();
+    if (!(widen >= 1.0) || !(fallback >= widen)) return fail(EXQ_ERR_ARG, "exq_set_guard: need 1 <= widen <= fallback");
+    g.guard_widen = widen;
+    g.guard_fallback = fallback;
+    return EXQ_OK;
+}
+int exq_guard_counts(int64_t* widened, int64_t* fallbacks) {
+    API_LOCK();
+    if (widened) *widened = g.guard_widened;
+    if (fallbacks) *fallbacks = g.guard_fallbacks;
+    return EXQ_OK;
+}
+int exq_gp_kappa(exq_gp_t gp, double* kappa, int* on_fp64) {
+    REQUIRE_READY();
+    if (!gp) return fail(EXQ_ERR_ARG, "exq_gp_kappa: bad argument");
+    if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_kappa: GP has not been fitted");
+    if (kappa) *kappa = gp->kappa;
+    if (on_fp64) *on_fp64 = gp->fit_on_dmma ? 1 : 0;
+    return EXQ_OK;
+}
+double exq_int8_gemm_ops(int M, int N, int K, int B, int krange, int lower_only, int digits) {
+    if (M < 128 || N < 64 || K < 64 || (M % 128) || (N % 64) || (K % 64) || B < 1 || digits < 1 || krange < 0 || krange > 4)
+        return -1.0;
+    return oz::gemm_issued_ops(M, N, K, B, krange, lower_only, digits);
+}
 
 int exq_timer_start(void) {
     REQUIRE_READY();
@@ -959,9 +1096,10 @@ int exq_gp_create(int64_t N, int d, const double* X, const double* y, int kernel
 }
 
 int exq_gp_destroy(exq_gp_t gp) {
+    API_LOCK();
     if (!gp) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
-    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep); cudaFree(gp->zsmall);
+    cudaFree(gp->X); cudaFree(gp->y); cudaFree(gp->rep); cudaFree(gp->zsmall); cudaFree(gp->small_x); cudaFree(gp->small_out);
     planes_park(gp->linv_planes, gp->linv_planes_bytes);
     cudaFree(gp->linv_exp);
     sys_release(gp->fit);
@@ -975,10 +1113,10 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
     REQUIRE_READY();
     if (!gp || !corr_raw || !(cov > 0.0) || nugget < 0.0) return fail(EXQ_ERR_ARG, "exq_gp_fit: bad argument");
     const int d = gp->d;
+    gp->fitted = false;   // before anything can fail: a failed refit must not leave the old state looking valid
+    gp->planes_S = 0;
     int rc = sys_alloc(gp->fit, 1, (int)gp->N, d, false, false);
     if (rc) return rc;
-    gp->fitted = false;
-    gp->planes_S = 0;
     std::vector<double> th(d + 2);
     for (int k = 0; k < d; k++) {
         th[k] = exp(corr_raw[k]);
@@ -988,19 +1126,39 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
     double nug = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 0.0 : nugget;
     std::vector<int> info;
     const int max_tries = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 6 : 1;
-    bool ok = false;
-    for (int attempt = 0; attempt < max_tries; attempt++) {
-        th[d + 1] = nug;
-        if ((rc = upload_theta(gp->fit, th))) return rc;
-        if ((rc = assemble_and_factor(gp->fit, gp->X, 0, (int)gp->N, gp->kernel_id, info))) return rc;
-        if (info[0] == 0) { ok = true; break; }
-        nug = (attempt == 0) ? cov * 1e-6 : nug * 10.0;   // mogp jit_cholesky
+    double ldq[2], dst[2];
+    gp->fit_on_dmma = false;
+    for (int pass = 0; pass < 2; pass++) {
+        // pass 1 only when the conditioning guard rejects an int8 factorisation: same system on FP64 DMMA
+        g.oz_off = (pass == 1);
+        nug = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 0.0 : nugget;
+        bool ok = false;
+        for (int attempt = 0; attempt < max_tries; attempt++) {
+            th[d + 1] = nug;
+            if ((rc = upload_theta(gp->fit, th))) break;
+            if ((rc = assemble_and_factor(gp->fit, gp->X, 0, (int)gp->N, gp->kernel_id, info))) break;
+            if (info[0] == 0) { ok = true; break; }
+            nug = (attempt == 0) ? cov * 1e-6 : nug * 10.0;   // mogp jit_cholesky
+        }
+        if (!rc && !ok) rc = fail(EXQ_NOT_PD, "covariance matrix is not positive definite");
+        if (!rc) rc = solve_vectors(gp->fit, gp->y, 0, (int)gp->N);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(ldq, gp->fit.ldq, sizeof(ldq), cudaMemcpyDeviceToHost, g.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, gp->fit.dstat, sizeof(dst), cudaMemcpyDeviceToHost, g.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+            if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_fit: ") + cudaGetErrorString(e));
+        }
+        const bool was_int8 = factor_uses_int8(gp->fit);
+        g.oz_off = false;
+        if (rc) return rc;
+        gp->kappa = (dst[0] > 0.0) ? (dst[1] / dst[0]) * (dst[1] / dst[0]) : INFINITY;
+        if (pass == 0 && was_int8 && !(gp->kappa < g.guard_fallback)) {
+            g.guard_fallbacks++;
+            gp->fit_on_dmma = true;
+            continue;
+        }
+        break;
     }
-    if (!ok) return fail(EXQ_NOT_PD, "covariance matrix is not positive definite");
-    if ((rc = solve_vectors(gp->fit, gp->y, 0, (int)gp->N))) return rc;
-    double ldq[2];
-    CUDA_TRY(cudaMemcpyAsync(ldq, gp->fit.ldq, sizeof(ldq), cudaMemcpyDeviceToHost, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
     gp->fitted = true;
     gp->cov = cov;
     gp->nugget = nug;
@@ -1015,6 +1173,21 @@ int exq_gp_predict(exq_gp_t gp, const double* Xc, int64_t M, double* mean, doubl
     REQUIRE_READY();
     if (!gp || !Xc || M < 1) return fail(EXQ_ERR_ARG, "exq_gp_predict: bad argument");
     if (!gp->fitted) return fail(EXQ_ERR_STATE, "exq_gp_predict: GP has not been fitted");
+    if (M <= 128) {
+        // scalar / few-point calls (PEICalculator.compute through the unchanged maximise: one predict per objective
+        // evaluation, exauq/core/designers.py:522-706): no allocation, one upload, one download
+        int rc = ensure_small_scratch(gp);
+        if (rc) return rc;
+        const int d = gp->d;
+        CUDA_TRY(cudaMemsetAsync(gp->small_x, 0, (size_t)128 * d * sizeof(double), g.stream));
+        CUDA_TRY(cudaMemcpyAsync(gp->small_x, Xc, (size_t)M * d * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        rc = predict_device(gp, gp->small_x, M, 128, nullptr, 0, 0.0, 0, gp->small_out, gp->small_out + 128, nullptr);
+        if (rc) return rc;
+        if (mean) CUDA_TRY(cudaMemcpyAsync(mean, gp->small_out, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        if (var) CUDA_TRY(cudaMemcpyAsync(var, gp->small_out + 128, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        return EXQ_OK;
+    }
     exq_cand_t c = nullptr;
     int rc = exq_cand_create(M, gp->d, Xc, &c);
     if (rc) return rc;
@@ -1034,7 +1207,13 @@ int exq_gp_cross_cov(exq_gp_t gp, const double* Xq, int64_t n, double* out) {
     int rc = ensure_pred_scratch(gp, std::max<int64_t>(npad, 128));
     if (rc) return rc;
     double* xq = nullptr;
-    CUDA_TRY(cudaMalloc(&xq, (size_t)npad * d * sizeof(double)));
+    const bool small = npad <= 128;
+    if (small) {
+        if ((rc = ensure_small_scratch(gp))) return rc;
+        xq = gp->small_x;
+    } else {
+        CUDA_TRY(cudaMalloc(&xq, (size_t)npad * d * sizeof(double)));
+    }
     cudaError_t e = cudaMemsetAsync(xq, 0, (size_t)npad * d * sizeof(double), g.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(xq, Xq, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, g.stream);
     if (e == cudaSuccess) {
@@ -1048,7 +1227,7 @@ int exq_gp_cross_cov(exq_gp_t gp, const double* Xq, int64_t n, double* out) {
         e = cudaMemcpy2DAsync(out, (size_t)gp->N * sizeof(double), gp->KcT, (size_t)Np * sizeof(double),
                               (size_t)gp->N * sizeof(double), (size_t)n, cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-    cudaFree(xq);
+    if (!small) cudaFree(xq);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string("exq_gp_cross_cov: ") + cudaGetErrorString(e));
     return EXQ_OK;
@@ -1156,30 +1335,82 @@ int exq_gp_kinv(exq_gp_t gp, double* out) {
     Sys tmp;
     int rc = sys_alloc(tmp, 1, N, d, true, false);
     if (rc) { sys_free(tmp); return rc; }
+    const int Np = tmp.Np;
     std::vector<double> th(d + 2);
     for (int k = 0; k < d; k++) th[k] = exp(gp->corr_raw[k]);
     th[d] = gp->cov; th[d + 1] = 0.0;
     std::vector<int> info;
-    rc = upload_theta(tmp, th);
-    if (!rc) rc = assemble_and_factor(tmp, gp->X, 0, N, gp->kernel_id, info);
-    if (!rc && info[0] != 0) rc = fail(EXQ_NOT_PD, "Covariance Matrix is, or too close to singular.");
-    if (!rc) {
-        // cond_2(K) >= (max L_ii / min L_ii)^2: when even this lower bound reaches 1/eps the reference's
-        // check (np.linalg.cond(k) >= 1/eps, exauq/core/modelling.py:1082-1093) would refuse the matrix
+    const char* singular = "Covariance Matrix is, or too close to singular.";
+    double kappa = 1.0;
+    bool on_dmma = false;
+    for (int pass = 0; pass < 2 && !rc; pass++) {
+        g.oz_off = (pass == 1);                  // pass 1: the conditioning guard sends the factorisation to FP64 DMMA
+        rc = upload_theta(tmp, th);
+        if (!rc) rc = assemble_and_factor(tmp, gp->X, 0, N, gp->kernel_id, info);
+        const bool was_int8 = factor_uses_int8(tmp);
+        g.oz_off = false;
+        if (!rc && info[0] != 0) rc = fail(EXQ_NOT_PD, singular);
+        if (rc) break;
+        // cond_2(K) >= (max L_ii / min L_ii)^2: when even this lower bound reaches 1/eps the reference's check
+        // (np.linalg.cond(k) >= 1/eps, exauq/core/modelling.py:1082-1093) refuses the matrix
         std::vector<double> diag(N);
-        cudaError_t e = cudaMemcpy2DAsync(diag.data(), sizeof(double), tmp.A, (size_t)(tmp.Np + 1) * sizeof(double),
+        cudaError_t e = cudaMemcpy2DAsync(diag.data(), sizeof(double), tmp.A, (size_t)(Np + 1) * sizeof(double),
                                           sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, g.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_kinv: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) { rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_kinv: ") + cudaGetErrorString(e)); break; }
+        double lo = diag[0], hi = diag[0];
+        for (int i = 1; i < N; i++) { lo = std::min(lo, diag[i]); hi = std::max(hi, diag[i]); }
+        kappa = (lo > 0.0) ? (hi / lo) * (hi / lo) : INFINITY;
+        if (!(kappa < 1.0 / 2.220446049250313e-16)) { rc = fail(EXQ_NOT_PD, singular); break; }
+        if (pass == 0 && was_int8 && kappa >= g.guard_fallback) {
+            g.guard_fallbacks++;
+            on_dmma = true;
+            continue;
+        }
+        break;
+    }
+    if (!rc) {
+        // 2-norm condition estimate, the quantity the reference thresholds: lambda_max(K) by power iteration on a
+        // freshly assembled K (in W, free until LAUUM), lambda_max(K^-1) = |Linv|_2^2 by power iteration on
+        // Linv^T Linv.  Both converge from below, so cond is never over-estimated (no false refusals).
+        AsmArgs a{};
+        a.Xi = gp->X; a.Xj = gp->X; a.theta = tmp.theta; a.out = tmp.W;
+        a.ld = Np; a.n_i = N; a.n_j = N; a.d = d; a.kernel_id = gp->kernel_id; a.sym = 0; a.scale_sigma2 = 1;
+        rc = launch_assemble(a, Np, Np, 1);
+        double lmax_k = 0.0, lmax_inv = 0.0;
+        const int iters = 40;
+        if (!rc)
+            rc = power_iteration(
+                [&](double* x, double* y) {
+                    gemv_kernel<<<Np / 8, 256, 0, g.stream>>>(tmp.W, Np, x, y, Np);
+                    return EXQ_OK;
+                },
+                tmp.tvec, tmp.kvec, tmp.ldq, Np, N, iters, &lmax_k);
+        if (!rc)
+            rc = power_iteration(
+                [&](double* x, double* y) {
+                    trmv_lower_kernel<<<dim3(Np / 8, 1, 1), 256, 0, g.stream>>>(tmp.Linv, Np, 0, x, 0, tmp.alpha, 0, Np);
+                    trmv_lower_t_kernel<<<dim3(Np / 32, TRMV_T_SPLITS, 1), 256, 0, g.stream>>>(tmp.Linv, Np, 0, tmp.alpha, 0,
+                                                                                              tmp.tpart, Np);
+                    trmv_t_reduce_kernel<<<dim3((Np + 255) / 256, 1, 1), 256, 0, g.stream>>>(tmp.tpart, y, tmp.dinv, 0, Np);
+                    g.launches += 2;
+                    return EXQ_OK;
+                },
+                tmp.tvec, tmp.kvec, tmp.ldq, Np, N, iters, &lmax_inv);
+        // (padding: K assembled with sym = 0 is zero there and Linv is the identity there with no coupling to the real
+        // block, so a start vector that vanishes on the padding stays in the real subspace)
         if (!rc) {
-            double lo = diag[0], hi = diag[0];
-            for (int i = 1; i < N; i++) { lo = std::min(lo, diag[i]); hi = std::max(hi, diag[i]); }
-            const double ratio = hi / lo;
-            if (!(lo > 0.0) || ratio * ratio >= 1.0 / 2.220446049250313e-16)
-                rc = fail(EXQ_NOT_PD, "Covariance Matrix is, or too close to singular.");
+            const double cond2 = std::max(lmax_k * lmax_inv, kappa);
+            if (!(cond2 < 1.0 / 2.220446049250313e-16)) rc = fail(EXQ_NOT_PD, singular);
         }
     }
-    if (!rc) rc = lauum(tmp);
+    if (!rc) {
+        // kinv is multiplied into 1e-8-tolerance quantities by the unchanged multi-level path
+        // (exauq/core/designers.py:1029): always 7 digits on the int8 path, FP64 DMMA when the guard says so
+        g.oz_off = on_dmma;
+        rc = lauum(tmp, 7);
+        g.oz_off = false;
+    }
     if (!rc) {
         cudaError_t e = cudaMemcpy2DAsync(out, (size_t)N * sizeof(double), tmp.W, (size_t)tmp.Np * sizeof(double),
                                           (size_t)N * sizeof(double), (size_t)N, cudaMemcpyDeviceToHost, g.stream);
@@ -1235,36 +1466,42 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
             thb[(size_t)b * (d + 2) + d] = cv;
             thb[(size_t)b * (d + 2) + d + 1] = nug[b];
         }
-        // The systems are split into groups that are enqueued on separate streams: while one group is
-        // in the latency-bound bottom of its recursion (a handful of CTAs), another group's large GEMMs
-        // fill the SMs.  Failed factorisations (adaptive nugget) are retried group by group.
+        // Phase A (all systems of the pass in every launch): assembly, potrf + trtri, alpha / logdet / quad.  The
+        // host then reads info[] and the diag(L) range: failed factorisations are retried system by system with the
+        // next jitter (adaptive nugget); systems whose conditioning proxy reaches guard_fallback are re-factored on
+        // the FP64 DMMA path.  Phase B (LAUUM + gradient contraction) runs for the systems that are positive
+        // definite, with 7 instead of 6 digits when any of them reaches guard_widen.  The one extra host round trip
+        // between the phases costs ~30 us against >= 5 ms of device work per round.
         std::vector<int> info(B, 0);
+        std::vector<double> dst((size_t)B * 2, 1.0);
+        std::vector<char> on_dmma(B, 0);
         const int max_tries = (nugget_mode == EXQ_NUGGET_ADAPTIVE) ? 6 : 1;
-        const int ngroups = std::max(1, std::min(g.eval_streams, B / 3));
-        cudaStream_t main_stream = g.stream;
+        const bool int8_factor = factor_uses_int8(s);
+        auto read_state = [&]() -> int {
+            cudaError_t e = cudaMemcpyAsync(info.data(), s.info, B * sizeof(int), cudaMemcpyDeviceToHost, g.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst.data(), s.dstat, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, g.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+            if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string("exq_gp_logpost_batch: ") + cudaGetErrorString(e));
+            return EXQ_OK;
+        };
+        auto kappa_of = [&](int b) {
+            const double lo = dst[2 * b], hi = dst[2 * b + 1];
+            return (lo > 0.0) ? (hi / lo) * (hi / lo) : INFINITY;
+        };
         for (int attempt = 0; attempt < max_tries && !rc; attempt++) {
             std::vector<std::pair<int, int>> groups;     // (first system, count) still to be evaluated
             if (attempt == 0) {
-                for (int k = 0; k < ngroups; k++) {
-                    int lo = (int)((int64_t)B * k / ngroups), hi = (int)((int64_t)B * (k + 1) / ngroups);
-                    if (hi > lo) groups.emplace_back(lo, hi - lo);
-                }
+                groups.emplace_back(0, B);
             } else {
                 for (int b = 0; b < B; b++)
                     if (info[b] != 0) groups.emplace_back(b, 1);
             }
             for (size_t k = 0; k < groups.size() && !rc; k++) {
-                g.stream = (k % ngroups == 0) ? main_stream : g.side[(k % ngroups) - 1];
                 Sys v = sys_view(s, groups[k].first, groups[k].second, dmax);
-                rc = enqueue_logpost(gp, v, thb.data() + (size_t)groups[k].first * (d + 2), grad != nullptr, dmax);
+                rc = enqueue_factor(gp, v, thb.data() + (size_t)groups[k].first * (d + 2));
             }
-            g.stream = main_stream;
-            cudaError_t e = cudaStreamSynchronize(main_stream);
-            for (auto st : g.side)
-                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (!rc && e != cudaSuccess) rc = fail(EXQ_ERR_CUDA, std::string("exq_gp_logpost_batch: ") + cudaGetErrorString(e));
+            if (!rc) rc = read_state();
             if (rc) break;
-            CUDA_TRY(cudaMemcpy(info.data(), s.info, B * sizeof(int), cudaMemcpyDeviceToHost));
             bool any = false;
             for (int b = 0; b < B; b++) {
                 if (info[b] != 0 && attempt + 1 < max_tries) {
@@ -1275,6 +1512,38 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
                 }
             }
             if (!any) break;
+        }
+        // conditioning guard: badly conditioned systems leave the int8 path
+        if (!rc && int8_factor) {
+            bool redo = false;
+            for (int b = 0; b < B && !rc; b++) {
+                if (bad[b] || info[b] != 0 || kappa_of(b) < g.guard_fallback) continue;
+                g.guard_fallbacks++;
+                on_dmma[b] = 1;
+                g.oz_off = true;
+                Sys v = sys_view(s, b, 1, dmax);
+                rc = enqueue_factor(gp, v, thb.data() + (size_t)b * (d + 2));
+                g.oz_off = false;
+                redo = true;
+            }
+            if (!rc && redo) rc = read_state();
+        }
+        if (!rc && grad) {
+            int lauum_digits = 0;
+            for (int b = 0; b < B; b++)
+                if (!bad[b] && info[b] == 0 && !on_dmma[b] && kappa_of(b) >= g.guard_widen) lauum_digits = 7;
+            if (lauum_digits == 7 && int8_factor && g.oz_lauum_slices < 7) g.guard_widened++;
+            // maximal runs of systems that share a path: int8 (positive definite, not guarded) or FP64 DMMA
+            for (int b = 0; b < B && !rc;) {
+                if (bad[b] || info[b] != 0) { b++; continue; }
+                int e = b + 1;
+                while (e < B && !bad[e] && info[e] == 0 && on_dmma[e] == on_dmma[b]) e++;
+                Sys v = sys_view(s, b, e - b, dmax);
+                g.oz_off = on_dmma[b] != 0;
+                rc = enqueue_grad(gp, v, dmax, lauum_digits);
+                g.oz_off = false;
+                b = e;
+            }
         }
         std::vector<double> ldq((size_t)B * 2), gh((size_t)B * (d + 2));
         if (!rc) {
@@ -1352,6 +1621,7 @@ int exq_cand_set_points(exq_cand_t c, const double* Xc) {
 }
 
 int exq_cand_destroy(exq_cand_t c) {
+    API_LOCK();
     if (!c) return EXQ_OK;
     if (g.ready) cudaStreamSynchronize(g.stream);
     if (g.ready && !g_cand_parked && c->Mpad >= 65536) {   // park large sets for reuse
@@ -1393,6 +1663,8 @@ int exq_pei_argmax(exq_cand_t c, int64_t* idx, double* val) {
     ArgPair h;
     CUDA_TRY(cudaMemcpyAsync(&h, c->best, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
+    if (h.i < 0 || h.i >= c->M)
+        return fail(EXQ_ERR_STATE, "exq_pei_argmax: no finite pseudo-expected improvement among the candidates");
     if (idx) *idx = h.i;
     if (val) *val = h.v;
     return EXQ_OK;
@@ -1422,7 +1694,7 @@ int exq_pei_batch(exq_gp_t gp, exq_cand_t c, int batch_size, int64_t* idx, doubl
     }
     for (int s = 0; s < batch_size; s++) {
         ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
-        select_best_kernel<<<1, 64, 0, g.stream>>>(c->best, c->Xc, c->d, c->xnew, c->chosen, s);
+        select_best_kernel<<<1, 64, 0, g.stream>>>(c->best, c->Xc, c->M, c->d, c->xnew, c->chosen, s);
         prof_end(m);
         LAUNCH_CHECK("select_best_kernel");
         int rc = pei_argmax_launch(gp, c, c->xnew);
@@ -1432,6 +1704,8 @@ int exq_pei_batch(exq_gp_t gp, exq_cand_t c, int batch_size, int64_t* idx, doubl
     CUDA_TRY(cudaMemcpyAsync(h.data(), c->chosen, batch_size * sizeof(ArgPair), cudaMemcpyDeviceToHost, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     for (int s = 0; s < batch_size; s++) {
+        if (h[s].i < 0 || h[s].i >= c->M)
+            return fail(EXQ_ERR_STATE, "exq_pei_batch: no finite pseudo-expected improvement among the candidates");
         if (idx) idx[s] = h[s].i;
         if (val) val[s] = h[s].v;
     }

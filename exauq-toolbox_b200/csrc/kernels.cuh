@@ -198,29 +198,73 @@ __global__ void trmv_t_reduce_kernel(const double* __restrict__ part, double* __
     dinv[(int64_t)blockIdx.z * strideV + j] = sd;
 }
 
-// logdet = 2 sum_{i<N} log L_ii ; quad = y^T alpha.   out[b] = {logdet, quad}
+// logdet = 2 sum_{i<N} log L_ii ; quad = y^T alpha.   out[b] = {logdet, quad};  dstat[b] = {min_i L_ii, max_i L_ii}
+// (max/min)^2 is a lower bound of cond_2(K): the conditioning proxy of the int8 digit guard (exq_api.cu)
 __global__ void __launch_bounds__(256) logdet_quad_kernel(const double* __restrict__ A, int64_t ld,
                                                           int64_t strideA, const double* __restrict__ y,
                                                           int64_t strideY, const double* __restrict__ alpha,
-                                                          int64_t strideV, int N, double* __restrict__ out) {
-    __shared__ double r1[8], r2[8];
+                                                          int64_t strideV, int N, double* __restrict__ out,
+                                                          double* __restrict__ dstat) {
+    __shared__ double r1[8], r2[8], r3[8], r4[8];
     const double* a = A + (int64_t)blockIdx.x * strideA;
     const double* yy = y + (int64_t)blockIdx.x * strideY;
     const double* al = alpha + (int64_t)blockIdx.x * strideV;
-    double s1 = 0.0, s2 = 0.0;
+    double s1 = 0.0, s2 = 0.0, lo = CUDART_INF, hi = 0.0;
     for (int i = threadIdx.x; i < N; i += 256) {
-        s1 += log(a[(int64_t)i * ld + i]);
+        const double l = a[(int64_t)i * ld + i];
+        s1 += log(l);
         s2 += yy[i] * al[i];
+        lo = fmin(lo, l);
+        hi = fmax(hi, l);
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
-    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; r3[threadIdx.x >> 5] = lo; r4[threadIdx.x >> 5] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < 8; k++) { s1 += r1[k]; s2 += r2[k]; }
+        for (int k = 1; k < 8; k++) { s1 += r1[k]; s2 += r2[k]; lo = fmin(lo, r3[k]); hi = fmax(hi, r4[k]); }
         out[2 * blockIdx.x] = 2.0 * s1;
         out[2 * blockIdx.x + 1] = s2;
+        dstat[2 * blockIdx.x] = lo;
+        dstat[2 * blockIdx.x + 1] = hi;
     }
+}
+
+// y = M x for a dense row-major n x n matrix (one warp per row): power iteration of the kinv condition estimate
+__global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ Mx, int64_t ld, const double* __restrict__ x,
+                                                   double* __restrict__ yout, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= n) return;
+    const double* row = Mx + (int64_t)i * ld;
+    double s = 0.0;
+    for (int k = lane; k < n; k += 32) s = fma(row[k], x[k], s);
+    s = warp_sum(s);
+    if (lane == 0) yout[i] = s;
+}
+
+// x <- x / |x|_2 ; norm_out[0] = |x|_2 (one block)
+__global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ x, int n, double* __restrict__ norm_out) {
+    __shared__ double red[8];
+    __shared__ double nrm;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s = fma(x[i], x[i], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) s += red[k];
+        nrm = sqrt(s);
+        norm_out[0] = nrm;
+    }
+    __syncthreads();
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) x[i] *= inv;
 }
 
 // =====================================================================================
@@ -594,10 +638,12 @@ __global__ void grad_reduce_kernel(const double* __restrict__ partial, int ntile
 }
 
 // record the current best candidate as chosen[step] and stage its coordinates as x_new
-__global__ void select_best_kernel(const ArgPair* __restrict__ best, const double* __restrict__ Xc, int d,
+// (an arg max over values that are all NaN leaves the sentinel index: nothing is read through it; the host reports it)
+__global__ void select_best_kernel(const ArgPair* __restrict__ best, const double* __restrict__ Xc, long long M, int d,
                                    double* __restrict__ xnew, ArgPair* __restrict__ chosen, int step) {
     long long bi = best->i;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) xnew[k] = Xc[bi * d + k];
+    if (bi >= 0 && bi < M)
+        for (int k = threadIdx.x; k < d; k += blockDim.x) xnew[k] = Xc[bi * d + k];
     if (threadIdx.x == 0) chosen[step] = *best;
 }
 

@@ -166,12 +166,33 @@ struct GArgs {
 };
 
 // k-block range [lo, hi) of output tile (I: 128 rows, J: 64 columns)
-__device__ __forceinline__ void tile_krange(int krange, int I, int J, int nkb, int& lo, int& hi) {
+__host__ __device__ __forceinline__ void tile_krange(int krange, int I, int J, int nkb, int& lo, int& hi) {
     lo = 0; hi = nkb;
-    if (krange == KR_LE_J) hi = min(nkb, J + 1);
+    if (krange == KR_LE_J) hi = nkb < J + 1 ? nkb : J + 1;
     else if (krange == KR_GE_J) lo = J;
-    else if (krange == KR_LE_I) hi = min(nkb, 2 * I + 2);
+    else if (krange == KR_LE_I) hi = nkb < 2 * I + 2 ? nkb : 2 * I + 2;
     else if (krange == KR_GE_I) lo = 2 * I;
+}
+__host__ __device__ __forceinline__ bool tile_skipped(int lower_only, int I, int J) {
+    return lower_only && J * BLK_R > I * BLK_C + (BLK_C - 1);
+}
+// k blocks (64 bytes of k for a 128 x 64 output tile) the kernel walks for one system: the SAME tile walk as
+// decode_gemm_item / tile_krange, so that the int8 operation count of the roofline is what was issued
+inline int64_t gemm_kblocks(int M, int N, int K, int krange, int lower_only) {
+    const int nI = M / BLK_C, nJ = N / BLK_R, nkb = K / BLK_K;
+    int64_t total = 0;
+    for (int I = 0; I < nI; I++)
+        for (int J = 0; J < nJ; J++) {
+            if (tile_skipped(lower_only, I, J)) continue;
+            int lo, hi;
+            tile_krange(krange, I, J, nkb, lo, hi);
+            if (hi > lo) total += hi - lo;
+        }
+    return total;
+}
+// int8 operations (2 per multiply-accumulate) issued for B systems with S digits: S(S+1)/2 digit products per k block
+inline double gemm_issued_ops(int M, int N, int K, int B, int krange, int lower_only, int S) {
+    return 2.0 * BLK_C * BLK_R * BLK_K * (double)gemm_kblocks(M, N, K, krange, lower_only) * B * (S * (S + 1) / 2);
 }
 // linear item -> (system, I, J); returns false for tiles skipped by lower_only.
 // sys_slow = 1 (full products): systems are the SLOW index, so the CTAs running at any moment work on one
@@ -195,7 +216,7 @@ __device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& 
     if (a.heavy_last) t = tiles - 1 - t;
     I = t / nJ;
     J = t - I * nJ;
-    return !(a.lower_only && J * BLK_R > I * BLK_C + (BLK_C - 1));
+    return !tile_skipped(a.lower_only, I, J);
 }
 
 template <int S>

@@ -167,12 +167,20 @@ def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats
 def global_argmax(cand, comm, candidate_offset: int, scale: float = 1.0, stats: Optional[dict] = None):
     """(value * scale, global index, point) of the best candidate over all ranks."""
     t0 = time.perf_counter()
-    i, v = cand.argmax()
+    err = None
+    try:
+        i, v = cand.argmax()
+    except Exception as exc:            # e.g. every PEI value on this rank is NaN
+        if comm.size == 1:
+            raise
+        err, i, v = exc, 0, float("nan")
     if comm.size == 1:
         return v * scale, i + candidate_offset, np.array(cand.Xc[i], dtype=float)
     msg = np.concatenate([[v * scale, float(i + candidate_offset)], cand.Xc[i]])
     t1 = time.perf_counter()
-    allm = comm.allgather(msg)
+    allm = comm.allgather(msg)      # every rank reaches the collective before anyone raises
+    if np.all(np.isnan(allm[:, 0])):
+        raise err if err is not None else RuntimeError("no finite pseudo-expected improvement on any rank")
     if stats is not None:
         stats["pei_argmax_s"] = stats.get("pei_argmax_s", 0.0) + (t1 - t0)
         stats["pei_allgather_s"] = stats.get("pei_allgather_s", 0.0) + (time.perf_counter() - t1)

@@ -65,6 +65,21 @@ int exq_set_int8_digits(int variance_digits, int factor_digits);
 /* number of kernels this library launched since process start (bench.py "gpu_launches") */
 int64_t exq_launch_count(void);
 
+/* Conditioning guard of the int8 paths.  kappa = (max L_ii / min L_ii)^2 -- a lower bound of cond_2(K) -- is read
+ * back with every factorisation.  kappa >= widen: products configured with 6 digits (variance, LAUUM) run with 7;
+ * kappa >= fallback: the factorisation is redone on the FP64 DMMA path and the system stays there.  Defaults
+ * 2^20 and 1e12 (EXQ_GUARD_WIDEN / EXQ_GUARD_FALLBACK).  The reference has no counterpart: LAPACK's FP64 dpotrf
+ * (mogp GaussianProcess.fit via exauq/core/emulators.py:447-448) is what the guard falls back towards. */
+int exq_set_guard(double widen, double fallback);
+int exq_guard_counts(int64_t* widened, int64_t* fallbacks); /* how often each rule fired since exq_init */
+/* kappa of the last exq_gp_fit of this handle and whether the guard sent that fit to FP64 DMMA */
+int exq_gp_kappa(exq_gp_t gp, double* kappa, int* on_fp64);
+/* int8 operations (2 per multiply-accumulate) oz::gemm_kernel issues for B systems of an M x N x K product with
+ * `digits` base-256 digits: the kernel's own tile walk (128 x 64 tiles, 64-byte k blocks, triangular k ranges
+ * krange = 0 full, 1 k <= j, 2 k >= j, 3 k <= i, 4 k >= i; lower_only skips tiles above the diagonal).  Host
+ * arithmetic only -- the roofline's operation count, exposed so that tests can re-derive it.  < 0: bad shape. */
+double exq_int8_gemm_ops(int M, int N, int K, int B, int krange, int lower_only, int digits);
+
 /* CUDA-event timing on the library stream (bench.py / roofline).  exq_timer_* brackets a
  * region; exq_prof_* accumulates per-class kernel time between reset and get. */
 int exq_timer_start(void);
