@@ -36,6 +36,7 @@ SIGNATURES = {
     "exq_launch_count": (C.c_int64, []),
     "exq_set_guard": (C.c_int, [C.c_double, C.c_double]),
     "exq_guard_counts": (C.c_int, [_lp, _lp]),
+    "exq_set_refine_steps": (C.c_int, [C.c_int]),
     "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
     "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "exq_timer_start": (C.c_int, []),
@@ -349,10 +350,16 @@ def factor_slices() -> int:
     return int(load().exq_factor_slices())
 
 
-def set_guard(widen: float = 2.0 ** 20, fallback: float = 1e12) -> None:
+def set_guard(widen: float = 2.0 ** 16, fallback: float = 1e12) -> None:
     """Thresholds of the conditioning guard of the int8 paths (see include/exauq_b200.h)."""
     init()
     check(load().exq_set_guard(float(widen), float(fallback)), "exq_set_guard")
+
+
+def set_refine_steps(steps: int = 1) -> None:
+    """Iterative-refinement steps of alpha after an int8 factorisation (0 = off)."""
+    init()
+    check(load().exq_set_refine_steps(int(steps)), "exq_set_refine_steps")
 
 
 def guard_counts() -> tuple[int, int]:

@@ -74,9 +74,10 @@ struct Ctx {
     //   kappa >= guard_widen    : 6-digit products (variance, LAUUM, kinv) are run with 7 digits (56 bits)
     //   kappa >= guard_fallback : the factorisation itself is redone on the FP64 DMMA path and everything
     //                             downstream (variance, LAUUM) stays on FP64 DMMA for that system
-    double guard_widen = 1048576.0;        // 2^20   (EXQ_GUARD_WIDEN)
+    double guard_widen = 65536.0;          // 2^16   (EXQ_GUARD_WIDEN)
     double guard_fallback = 1.0e12;        //        (EXQ_GUARD_FALLBACK)
     bool oz_off = false;                   // set while a guarded system is re-evaluated on FP64 DMMA
+    int refine_steps = 1;                  // iterative-refinement steps of alpha after an int8 factorisation (EXQ_REFINE_STEPS)
     int64_t guard_widened = 0, guard_fallbacks = 0;
 } g;
 
@@ -552,6 +553,41 @@ int solve_vectors(Sys& s, const double* y, int64_t strideY, int nvalid) {
     return EXQ_OK;
 }
 
+// `steps` steps of iterative refinement of alpha = K^-1 y on the systems of s (X, y as in solve_vectors), then
+// logdet / quad / diag(L) range again with the refined alpha.  r = y - K alpha from freshly evaluated covariance
+// entries; the correction Linv^T (Linv r) reuses the triangular mat-vec kernels (kvec / tvec as scratch).
+int refine_alpha(Sys& s, const double* X, int64_t strideX, const double* y, int64_t strideY, int nvalid, int kernel_id,
+                 int steps) {
+    const int64_t ld = s.Np, sq = s.sq();
+    const size_t smem = ((size_t)32 * s.d + s.d + 2) * sizeof(double);
+    for (int it = 0; it < steps; it++) {
+        ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)s.B * nvalid * nvalid * (3.0 * s.d + 32.0), 0.0);
+        kresidual_kernel<<<dim3(s.Np / 32, 1, s.B), 256, smem, g.stream>>>(X, strideX, s.theta, s.d + 2, y, strideY, s.alpha, s.Np,
+                                                                       s.kvec, nvalid, s.Np, s.d, kernel_id);
+        prof_end(m);
+        LAUNCH_CHECK("kresidual_kernel");
+        m = prof_begin(EXQ_PROF_STREAM, (double)s.B * s.Np * s.Np, (double)s.B * s.Np * s.Np * 4.0);
+        trmv_lower_kernel<<<dim3(s.Np / 8, 1, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, s.kvec, s.Np, s.tvec, s.Np, s.Np);
+        prof_end(m);
+        m = prof_begin(EXQ_PROF_STREAM, 2.0 * s.B * s.Np * s.Np, (double)s.B * s.Np * s.Np * 4.0);
+        trmv_lower_t_kernel<<<dim3(s.Np / 32, TRMV_T_SPLITS, s.B), 256, 0, g.stream>>>(s.Linv, ld, sq, s.tvec, s.Np, s.tpart, s.Np);
+        prof_end(m);
+        m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+        // the reduce kernel rewrites dinv with the same column sums of squares as before (they do not depend on the vector)
+        trmv_t_reduce_kernel<<<dim3((s.Np + 255) / 256, 1, s.B), 256, 0, g.stream>>>(s.tpart, s.kvec, s.dinv, s.Np, s.Np);
+        prof_end(m);
+        m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+        axpy_kernel<<<dim3((nvalid + 255) / 256, 1, s.B), 256, 0, g.stream>>>(s.alpha, s.kvec, s.Np, nvalid);
+        prof_end(m);
+        LAUNCH_CHECK("alpha refinement");
+    }
+    ProfMark m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
+    logdet_quad_kernel<<<s.B, 256, 0, g.stream>>>(s.A, ld, sq, y, strideY, s.alpha, s.Np, nvalid, s.ldq, s.dstat);
+    prof_end(m);
+    LAUNCH_CHECK("logdet_quad_kernel");
+    return EXQ_OK;
+}
+
 // K^-1 (lower tiles) into s.W; digits: base-256 digits of the int8 product (0: the configured LAUUM digits)
 int lauum(Sys& s, int digits = 0) {
     GemmArgs a{};
@@ -895,6 +931,7 @@ int exq_init(int device) {
     }
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_REFINE_STEPS")) g.refine_steps = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("EXQ_GUARD_WIDEN")) g.guard_widen = std::max(1.0, atof(e));
     if (const char* e = getenv("EXQ_GUARD_FALLBACK")) g.guard_fallback = std::max(g.guard_widen, atof(e));
     if (const char* e = getenv("EXQ_OZAKI_LAUUM_SLICES")) g.oz_lauum_slices = atoi(e) == 7 ? 7 : 6;
@@ -951,6 +988,12 @@ int exq_set_guard(double widen, double fallback) {
     if (!(widen >= 1.0) || !(fallback >= widen)) return fail(EXQ_ERR_ARG, "exq_set_guard: need 1 <= widen <= fallback");
     g.guard_widen = widen;
     g.guard_fallback = fallback;
+    return EXQ_OK;
+}
+int exq_set_refine_steps(int steps) {
+    REQUIRE_READY();
+    if (steps < 0 || steps > 4) return fail(EXQ_ERR_ARG, "exq_set_refine_steps: 0..4");
+    g.refine_steps = steps;
     return EXQ_OK;
 }
 int exq_guard_counts(int64_t* widened, int64_t* fallbacks) {
@@ -1142,6 +1185,9 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
         }
         if (!rc && !ok) rc = fail(EXQ_NOT_PD, "covariance matrix is not positive definite");
         if (!rc) rc = solve_vectors(gp->fit, gp->y, 0, (int)gp->N);
+        // alpha feeds every predictive mean: one refinement step whenever the inverse factor came from the int8 kernels
+        if (!rc && g.refine_steps > 0 && factor_uses_int8(gp->fit))
+            rc = refine_alpha(gp->fit, gp->X, 0, gp->y, 0, (int)gp->N, gp->kernel_id, g.refine_steps);
         if (!rc) {
             cudaError_t e = cudaMemcpyAsync(ldq, gp->fit.ldq, sizeof(ldq), cudaMemcpyDeviceToHost, g.stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(dst, gp->fit.dstat, sizeof(dst), cudaMemcpyDeviceToHost, g.stream);
@@ -1293,6 +1339,8 @@ int exq_gp_loo_refit(exq_gp_t gp, const int* idx, int cnt, double* mean, double*
             for (int b = 0; b < B; b++)
                 if (info[b] != 0) rc = fail(EXQ_NOT_PD, "LOO system not positive definite");
         if (!rc) rc = solve_vectors(s, s.yb, s.Np, Nm);
+        if (!rc && g.refine_steps > 0 && factor_uses_int8(s))
+            rc = refine_alpha(s, s.Xb, (int64_t)s.Np * d, s.yb, s.Np, Nm, gp->kernel_id, g.refine_steps);
         if (!rc) {
             m = prof_begin(EXQ_PROF_STREAM, (double)B * Nm * (3.0 * d + 30.0), (double)B * Nm * d * 8.0);
             loo_cross_vec_kernel<<<dim3((Npm + 255) / 256, B), 256, 0, g.stream>>>(

@@ -333,6 +333,56 @@ __device__ __forceinline__ double point_corr(int kernel_id, const double* __rest
     return corr_from_r2(kernel_id, r2);
 }
 
+// =====================================================================================
+// Iterative refinement of alpha = K^-1 y (exq_api.cu: refine_alpha).  r = y - (sigma2 C + nugget I) alpha with the
+// covariance entries recomputed from the points in FP64 (never read from the factorised copy), one 32-row slab per
+// CTA, 8 column lanes per row.  With the inverse factor built from int8 digit products the first alpha carries
+// errors that are small in norm but unstructured, and the predictive mean k^T alpha -- a sum with cond(K)-fold
+// cancellation -- showed them (tools/guard_survey.py: 4e-8 against 7e-10 on the FP64 DMMA path at cond 4e7); one
+// refinement step restores the backward-stable level.  Reference: mogp computes alpha by cho_solve in
+// GaussianProcess.fit (exauq/core/emulators.py:447-448).
+// =====================================================================================
+__global__ void __launch_bounds__(256) kresidual_kernel(const double* __restrict__ Xall, int64_t strideX,
+                                                        const double* __restrict__ thetaall, int64_t strideTheta,
+                                                        const double* __restrict__ yall, int64_t strideY,
+                                                        const double* __restrict__ alphaall, int64_t strideV,
+                                                        double* __restrict__ rall, int N, int Np, int d, int kernel_id) {
+    extern __shared__ double kr_smem[];   // Xi[32][d], w[d+2]
+    double* Xi_s = kr_smem;
+    double* w_s = kr_smem + 32 * d;
+    const double* X = Xall + (int64_t)blockIdx.z * strideX;
+    const double* theta = thetaall + (int64_t)blockIdx.z * strideTheta;
+    const double* y = yall + (int64_t)blockIdx.z * strideY;
+    const double* alpha = alphaall + (int64_t)blockIdx.z * strideV;
+    double* r = rall + (int64_t)blockIdx.z * strideV;
+    const int row0 = blockIdx.x * 32;
+    for (int e = threadIdx.x; e < 32 * d; e += 256) Xi_s[e] = (row0 + e / d < N) ? X[(int64_t)row0 * d + e] : 0.0;
+    if (threadIdx.x < d + 2) w_s[threadIdx.x] = theta[threadIdx.x];
+    __syncthreads();
+    const int lr = threadIdx.x >> 3, cl = threadIdx.x & 7;
+    const int i = row0 + lr;
+    const double sigma2 = w_s[d], nugget = w_s[d + 1];
+    double acc = 0.0;
+    if (i < N) {
+        const double* xi = Xi_s + lr * d;
+        for (int j = cl; j < N; j += 8) {
+            double cv = (j == i) ? 1.0 : point_corr(kernel_id, xi, X + (int64_t)j * d, w_s, d);
+            double kij = sigma2 * cv + ((j == i) ? nugget : 0.0);
+            acc = fma(kij, alpha[j], acc);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (cl == 0 && i < Np) r[i] = (i < N) ? y[i] - acc : 0.0;
+}
+
+// alpha += delta (padding untouched)
+__global__ void axpy_kernel(double* __restrict__ alpha, const double* __restrict__ delta, int64_t strideV, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) alpha[(int64_t)blockIdx.z * strideV + i] += delta[(int64_t)blockIdx.z * strideV + i];
+}
+
 __device__ __forceinline__ double expected_improvement(double mean, double var, double tmax) {
     double sd = sqrt(var);
     if (fabs(sd) <= 1e-9) return 0.0;          // equal_within_tolerance(sd, 0), numerics.py:31-73

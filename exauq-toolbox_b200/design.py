@@ -134,34 +134,75 @@ def pick_global_best(vals: np.ndarray, idxs: np.ndarray) -> int:
 # ---------------------------------------------------------------------------------------
 # shared steps
 # ---------------------------------------------------------------------------------------
-def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats):
+def fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats, restart_split: str = "per_rank"):
     """MAP fit of a GP to NES errors with the LOO length-scale bounds, restarts sharded over
-    ranks; every rank ends with the same fitted GP (compute_loo_errors_gp :274-276)."""
+    ranks; every rank ends with the same fitted GP (compute_loo_errors_gp :274-276).
+
+    ``restart_split="per_rank"`` (weak scaling): every rank draws its own ``n_tries`` starting points (seed offset
+    by the rank).  ``"global"`` (strong scaling): ``n_tries`` is the total -- every rank draws the same ``n_tries``
+    points from the same seed and owns points rank, rank + G, ...; the fitted GP is then the single-rank one
+    whatever the number of ranks.  Either way the objective evaluations of a round are spread evenly over all
+    ranks (``gp._evaluate_shared``)."""
     d = X.shape[1]
     gp_e = gp_factory(X, nes, kernel)
     priors = MapPriors(X)
-    if seed is not None:
-        np.random.seed(seed + 7919 * comm.rank)
-    starts = [priors.sample() for _ in range(n_tries)]
+    if restart_split == "global":
+        if seed is not None:
+            np.random.seed(seed)
+        every = [priors.sample() for _ in range(n_tries)]
+        mine = list(range(comm.rank, n_tries, comm.size))
+        starts = [every[i] for i in mine]
+        cap = (n_tries + comm.size - 1) // comm.size
+    else:
+        if seed is not None:
+            np.random.seed(seed + 7919 * comm.rank)
+        starts = [priors.sample() for _ in range(n_tries)]
+        mine = [comm.rank + comm.size * k for k in range(n_tries)]
+        cap = n_tries
     mstats: dict = {}
     results = run_map_restarts(gp_e, priors, starts, loo_error_raw_bounds(bounds), 0.0, True, stats=mstats,
-                               return_all=True)
-    done = [r for r in results if r is not None]
-    local = np.full(d + 2, np.inf)
-    if done:
-        k = int(np.argmin([r[0] for r in done]))
-        local[0], local[1:] = done[k][0], done[k][1]
+                               return_all=True, comm=comm, cap=cap)
+    local = np.full(d + 3, np.inf)           # (objective, global restart index, theta)
+    for k, r in enumerate(results):
+        if r is not None and (r[0] < local[0] or (r[0] == local[0] and mine[k] < local[1])):
+            local[0], local[1], local[2:] = r[0], float(mine[k]), r[1]
     tg = time.perf_counter()
     gathered = comm.allgather(local)
-    stats["map_allgather_wait_s"] = time.perf_counter() - tg   # includes waiting for the slowest rank's restarts
+    stats["map_allgather_wait_s"] = time.perf_counter() - tg
     if not np.any(np.isfinite(gathered[:, 0])):
         raise RuntimeError("GP fitting failed")
-    theta = gathered[int(np.argmin(gathered[:, 0])), 1:]
+    best = np.min(gathered[:, 0])
+    tied = np.nonzero(gathered[:, 0] == best)[0]
+    theta = gathered[int(tied[np.argmin(gathered[tied, 1])]), 2:]     # lowest restart index wins ties, as np.argmin does
     gp_e.fit(theta[:d], float(np.exp(theta[d])), 0.0, True)
     stats["map_batches"] = stats.get("map_batches", 0) + mstats.get("batches", 0)
     stats["map_evals"] = stats.get("map_evals", 0) + mstats.get("evals", 0)
     stats["map_gpu_s"] = stats.get("map_gpu_s", 0.0) + mstats.get("gpu_s", 0.0)
+    stats["map_comm_s"] = stats.get("map_comm_s", 0.0) + mstats.get("map_comm_s", 0.0)
+    stats["map_evals_here"] = stats.get("map_evals_here", 0) + mstats.get("evals_here", mstats.get("evals", 0))
     return gp_e, theta
+
+
+def loo_refit_sharded(gp, comm=None, indices=None):
+    """The reference's explicit leave-one-out loop (compute_loo_errors_gp, exauq/core/designers.py:263-272: one
+    fixed-hyperparameter refit per left-out point) sharded by left-out point: rank r refits the indices at
+    positions r, r + G, r + 2G, ... (block-cyclic, so that every rank sees the same mix of cheap and expensive
+    systems), then ONE all-gather of (mean, variance, NES) per index.  BASELINE.json configs[2]
+    (N = 8192, d = 10, 8192 refits over 2 / 4 / 8 B200).  ``gp`` is a fitted ``DeviceGP`` holding the same data on
+    every rank.  Returns (mean, var, nes) over ``indices`` (default: all N), identical on every rank."""
+    comm = comm or SingleComm()
+    idx = np.arange(gp.N, dtype=np.int32) if indices is None else np.ascontiguousarray(indices, dtype=np.int32)
+    n = idx.shape[0]
+    mine = idx[comm.rank :: comm.size]
+    share = (n + comm.size - 1) // comm.size
+    buf = np.full((share, 3), np.nan)
+    if mine.shape[0]:
+        m, v, e = gp.loo_refit(mine)
+        buf[: mine.shape[0], 0], buf[: mine.shape[0], 1], buf[: mine.shape[0], 2] = m, v, e
+    allb = comm.allgather(buf)                                # (G, share, 3)
+    pos = np.arange(n)
+    out = allb[pos % comm.size, pos // comm.size]
+    return out[:, 0].copy(), out[:, 1].copy(), out[:, 2].copy()
 
 
 def global_argmax(cand, comm, candidate_offset: int, scale: float = 1.0, stats: Optional[dict] = None):
@@ -228,13 +269,16 @@ def design_batch(
     gp_factory=DeviceGP,
     cand_factory=DeviceCandidates,
     stats: Optional[dict] = None,
+    restart_split: str = "per_rank",
+    explicit_loo: bool = False,
 ):
     """New design points for a GP with training data (X, y) and fitted hyperparameters.
 
     ``candidates`` is this rank's shard (array or device-resident candidate set) whose first
     row has global index ``candidate_offset``.  Returns ``(points[batch_size, d],
     global_indices[batch_size], pei_values[batch_size], errors_gp_theta_raw)``; identical on
-    every rank.
+    every rank.  ``restart_split``: see ``fit_errors_gp``.  ``explicit_loo``: run the reference's N explicit
+    refits sharded by left-out point (``loo_refit_sharded``) instead of the closed-form sweep.
     """
     comm = comm or SingleComm()
     X = np.ascontiguousarray(X, dtype=float)
@@ -247,13 +291,13 @@ def design_batch(
     corr_raw = -2.0 * np.log(np.asarray(corr_length_scales, dtype=float))
     gp = gp_factory(X, y, kernel)
     gp.fit(corr_raw, process_var, nugget)
-    _, _, nes = gp.loo()
+    _, _, nes = loo_refit_sharded(gp, comm) if explicit_loo else gp.loo()
     if not np.all(np.isfinite(nes)):
         raise FloatingPointError("non-finite NES error in the leave-one-out sweep")
 
     t1 = time.perf_counter()
     # 2. errors GP: MAP estimate, restarts sharded over ranks
-    gp_e, theta = fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats)
+    gp_e, theta = fit_errors_gp(X, nes, kernel, bounds, n_tries, seed, comm, gp_factory, stats, restart_split)
     t2 = time.perf_counter()
 
     # 3. PEI over this rank's candidates, batch_size rounds of arg max + repulsion update

@@ -68,10 +68,15 @@ int64_t exq_launch_count(void);
 /* Conditioning guard of the int8 paths.  kappa = (max L_ii / min L_ii)^2 -- a lower bound of cond_2(K) -- is read
  * back with every factorisation.  kappa >= widen: products configured with 6 digits (variance, LAUUM) run with 7;
  * kappa >= fallback: the factorisation is redone on the FP64 DMMA path and the system stays there.  Defaults
- * 2^20 and 1e12 (EXQ_GUARD_WIDEN / EXQ_GUARD_FALLBACK).  The reference has no counterpart: LAPACK's FP64 dpotrf
+ * 2^16 and 1e12 (EXQ_GUARD_WIDEN / EXQ_GUARD_FALLBACK).  The reference has no counterpart: LAPACK's FP64 dpotrf
  * (mogp GaussianProcess.fit via exauq/core/emulators.py:447-448) is what the guard falls back towards. */
 int exq_set_guard(double widen, double fallback);
 int exq_guard_counts(int64_t* widened, int64_t* fallbacks); /* how often each rule fired since exq_init */
+/* Steps of iterative refinement of alpha = K^-1 y after a factorisation that used the int8 kernels (default 1,
+ * EXQ_REFINE_STEPS; 0 switches it off): r = y - K alpha with K re-evaluated from the points in FP64,
+ * alpha += Linv^T Linv r.  Keeps the predictive mean k^T alpha (mogp GaussianProcess.predict,
+ * exauq/core/emulators.py:649) at the level of a backward-stable FP64 solve for ill-conditioned K. */
+int exq_set_refine_steps(int steps);
 /* kappa of the last exq_gp_fit of this handle and whether the guard sent that fit to FP64 DMMA */
 int exq_gp_kappa(exq_gp_t gp, double* kappa, int* on_fp64);
 /* int8 operations (2 per multiply-accumulate) oz::gemm_kernel issues for B systems of an M x N x K product with

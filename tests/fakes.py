@@ -30,6 +30,10 @@ class OracleGP:
     def predict(self, Xc):
         return orc.predict(self.gp, Xc)
 
+    def loo_refit(self, idx):
+        return orc.loo_refit(self.X, self.y, self.kernel, self.gp.theta.corr_raw, self.gp.theta.cov,
+                             float(self.gp.theta.nugget), [int(i) for i in idx])
+
     def logpost_batch(self, theta_raw, nugget=0.0, adaptive=False, want_grad=True):
         theta_raw = np.atleast_2d(theta_raw)
         self.n_batches += 1

@@ -25,14 +25,24 @@ comm = TorchComm()
 X, y = orc.synthetic_problem(40, 2)
 Xall = orc.synthetic_candidates(600, 2)
 shard = Xall[comm.rank * 300:(comm.rank + 1) * 300]
-# identical restarts on both ranks so that the fitted errors GP does not depend on the sharding
-class SameSeed:
-    rank, size = 0, comm.size
-    allgather, barrier = comm.allgather, comm.barrier
+# restart_split="global": the 3 restarts of the single-rank run, owned 2 + 1 by the two ranks; every round's objective
+# evaluations are shared out over both ranks (gp._evaluate_shared), so the fitted errors GP must be the single-rank one
+stats = {}
 pts, gidx, vals, theta = design_batch(X, y, "Matern52", [0.5, 0.5], 1.7, 0.0, [(0.0, 1.0)] * 2, shard, batch_size=4,
-                                      n_tries=3, seed=5, comm=SameSeed(), candidate_offset=comm.rank * 300,
-                                      gp_factory=OracleGP, cand_factory=OracleCandidates)
-json.dump({"pts": pts.tolist(), "gidx": gidx.tolist(), "vals": vals.tolist(), "theta": theta.tolist()},
+                                      n_tries=3, seed=5, comm=comm, candidate_offset=comm.rank * 300,
+                                      gp_factory=OracleGP, cand_factory=OracleCandidates, restart_split="global",
+                                      stats=stats)
+# the reference's explicit leave-one-out loop, sharded by left-out point (block-cyclic) + one all-gather
+from exauq_toolbox_b200.design import loo_refit_sharded
+gp = OracleGP(X, y, "Matern52").fit(-2 * np.log([0.5, 0.5]), 1.7, 0.0)
+lm, lv, ln = loo_refit_sharded(gp, comm)
+# weak-scaling mode: different restarts per rank, evaluations still shared; both ranks must end with the same GP
+pts2, gidx2, vals2, theta2 = design_batch(X, y, "Matern52", [0.5, 0.5], 1.7, 0.0, [(0.0, 1.0)] * 2, shard, batch_size=2,
+                                          n_tries=2, seed=5, comm=comm, candidate_offset=comm.rank * 300,
+                                          gp_factory=OracleGP, cand_factory=OracleCandidates)
+json.dump({"pts": pts.tolist(), "gidx": gidx.tolist(), "vals": vals.tolist(), "theta": theta.tolist(),
+           "loo": [lm.tolist(), lv.tolist(), ln.tolist()], "evals_here": stats["map_evals_here"], "evals_own": stats["map_evals"],
+           "theta2": theta2.tolist(), "gidx2": gidx2.tolist()},
           open(os.path.join(OUT, f"rank{comm.rank}.json"), "w"))
 dist.destroy_process_group()
 '''
@@ -73,6 +83,20 @@ def test_two_ranks_agree_with_single_rank(tmp_path):
                                           n_tries=3, seed=5, gp_factory=OracleGP, cand_factory=OracleCandidates)
     assert gidx.tolist() == r0["gidx"]
     assert np.allclose(vals, r0["vals"], rtol=1e-9) and np.allclose(pts, r0["pts"])
+    assert np.array_equal(theta, np.array(r0["theta"]))          # same optimiser trajectories, bit for bit
+    # evaluations were shared out: the rank that owns 2 of the 3 restarts did not do 2/3 of the work
+    total = r0["evals_own"] + r1["evals_own"]
+    assert r0["evals_here"] + r1["evals_here"] == total
+    assert abs(r0["evals_here"] - r1["evals_here"]) <= max(4, total // 8)
+    assert r0["evals_own"] > r1["evals_own"]
+    # sharded explicit LOO = the single-rank loop
+    gp = OracleGP(X, y, "Matern52").fit(-2 * np.log([0.5, 0.5]), 1.7, 0.0)
+    lm, lv, ln = gp.loo_refit(range(40))
+    for a, b in zip((lm, lv, ln), r0["loo"]):
+        assert np.allclose(a, b, rtol=1e-12, atol=0)
+    assert r0["loo"] == r1["loo"]
+    # weak mode: both ranks agree
+    assert r0["theta2"] == r1["theta2"] and r0["gidx2"] == r1["gidx2"]
 
 
 def test_pick_global_best_ties_and_nans():
