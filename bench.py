@@ -33,7 +33,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "pei_candidate_evals_per_s"
 UNIT = "candidates/s"
-NOMINAL_MAP_EVALS = 600  # 15 restarts x ~40 L-BFGS-B evaluations, used to extrapolate the CPU arm
+# Objective + gradient evaluations of the errors-GP MAP fit with 15 restarts on this workload, as the GPU arm
+# makes them (its L-BFGS-B iterates are bit-identical to scipy.optimize.minimize's, so the reference makes the
+# same number); the GPU arm prints its own count as map_fit.evals_per_step_per_gpu.  Used to extrapolate the CPU arm
+# (round 1 used a nominal 600, which inflated the MAP third of the CPU figure 1.8 x).
+MEASURED_MAP_EVALS_15_RESTARTS = 333
 
 
 def parse_args():
@@ -48,6 +52,8 @@ def parse_args():
     ap.add_argument("--batch-size", type=int, default=16)
     ap.add_argument("--restarts", type=int, default=15, help="MAP restarts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-path", action="store_true", help="reference arm: skip the one stock MogpEmulator.fit timing")
+    ap.add_argument("--strong-steps", type=int, default=5, help="timed steps of the strong-scaling sub-measurement (N > 1)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): --candidates and --restarts are per GPU; strong: they are totals split over the GPUs")
     return ap.parse_args()
@@ -57,7 +63,7 @@ def workload_config(a, n_gpus):
     return {
         "workload": (f"single-level design batch: N={a.n_train}, d={a.dim}, Matern-5/2 (l=0.5, var=1.7, nugget=0); "
                      f"LOO sweep + NES + errors-GP MAP fit ({a.restarts} restarts/GPU, bounded) + PEI over "
-                     f"{a.candidates} LHS candidates/GPU, batch_size={a.batch_size}"),
+                     f"{a.candidates} LHS candidates/GPU, batch_size={a.batch_size}; {n_gpus} GPU(s)"),
         "n_train": a.n_train, "dim": a.dim, "candidates_per_gpu": a.candidates,
         "candidates_total": a.candidates * n_gpus, "batch_size": a.batch_size,
         "restarts_per_gpu": a.restarts, "kernel": "Matern52",
@@ -122,7 +128,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU port of the reference path, timed on a bounded sample and extrapolated
 # ------------------------------------------------------------------------------------------
-def cpu_port_sample(a, X, y, Xc, n_refits=1, n_cand=1024, full_grad_terms=1):
+def cpu_port_sample(a, X, y, Xc, n_refits=1, n_cand=1024, full_grad_terms=1, n_gpus=1, map_evals=None):
     """Times the oracle (numpy/scipy restatement of the reference + mogp) on this box's host
     cores: ``n_refits`` fixed-hyperparameter LOO refits at full N, one log-posterior value and
     ``full_grad_terms`` of its d+1 gradient trace terms at full N, and PEI at ``n_cand``
@@ -148,15 +154,55 @@ def cpu_port_sample(a, X, y, Xc, n_refits=1, n_cand=1024, full_grad_terms=1):
     t0 = time.perf_counter()
     _ = orc.pei(gp, "Matern52", Xc[:n_cand], rep, float(y.max()))
     t["pei_per_candidate_s"] = (time.perf_counter() - t0) / n_cand
-    M = a.candidates
-    batch_s = (N * t["loo_refit_s"] + NOMINAL_MAP_EVALS * (t["logpost_value_s"] + (d + 1) * t["logpost_grad_term_s"])
+    # the workload of the GPU arm at n_gpus GPUs (weak scaling): n_gpus x candidates, n_gpus x restarts, one LOO sweep
+    M = a.candidates * n_gpus
+    if map_evals is None:
+        map_evals = int(round(MEASURED_MAP_EVALS_15_RESTARTS * a.restarts / 15.0)) * n_gpus
+    batch_s = (N * t["loo_refit_s"] + map_evals * (t["logpost_value_s"] + (d + 1) * t["logpost_grad_term_s"])
                + M * t["pei_per_candidate_s"])
     t["design_batch_s_extrapolated"] = batch_s
+    t["map_evals_assumed"] = map_evals
+    t["design_batch_s_extrapolated_closed_form_loo"] = batch_s - (N - 1) * t["loo_refit_s"]
     sample = (f"{n_refits} LOO refit(s) at N={N} (x N), 1 log-posterior value + {full_grad_terms} of {d + 1} gradient "
-              f"trace terms at N={N} (x {NOMINAL_MAP_EVALS} evaluations), PEI at {n_cand} candidates (x {M}/{n_cand}); "
-              "extrapolated linearly; excludes the reference's per-fit O(N^2) Python duplicate check and SVD/inv "
-              "(BASELINE.md section 3), i.e. favours the CPU")
+              f"trace terms at N={N} (x {map_evals} evaluations: the count the GPU arm makes), PEI at {n_cand} candidates "
+              f"(x {M}/{n_cand}); extrapolated linearly; excludes the reference's per-fit O(N^2) Python duplicate check "
+              "and SVD/inv (stock_path below prices them), i.e. favours the CPU; design_batch_s_extrapolated_closed_form_loo "
+              "= the same with ONE refit instead of N (what the GPU arm's closed-form sweep costs on the CPU)")
     return M / batch_s, t, sample
+
+
+def stock_path_sample(a, n_predict=20):
+    """ONE fit with given hyperparameters + scalar predictions through the UNMODIFIED reference classes from
+    baseline/_ref (exauq.core.emulators.MogpEmulator on the restated mogp of oracle/): what every one of the N
+    leave-one-out refits costs on the reference's stock path (duplicate check, Cholesky, SVD condition number,
+    explicit inverse: exauq/core/emulators.py:268-311, exauq/core/modelling.py:1082-1113).  Timed once."""
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "baseline", "_ref")):
+        if p not in sys.path and os.path.isdir(p):
+            sys.path.insert(0, p)
+    try:
+        from exauq.core.emulators import MogpEmulator, MogpHyperparameters
+        from exauq.core.modelling import Input, TrainingDatum
+    except Exception as exc:  # reference package not present on this box
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    from oracle import gp_oracle as orc
+
+    N, d = a.n_train, a.dim
+    X, y = orc.synthetic_problem(N, d)
+    data = [TrainingDatum(Input(*row), float(v)) for row, v in zip(X, y)]
+    gp = MogpEmulator(kernel="Matern52")
+    t0 = time.perf_counter()
+    gp.fit(data, hyperparameters=MogpHyperparameters(corr_length_scales=[0.5] * d, process_var=1.7, nugget=0.0))
+    fit_s = time.perf_counter() - t0
+    xs = [Input(*row) for row in orc.synthetic_candidates(n_predict, d)]
+    t0 = time.perf_counter()
+    for x in xs:
+        gp.predict(x)
+    pred_s = (time.perf_counter() - t0) / n_predict
+    return {"what": f"MogpEmulator.fit(hyperparameters=...) at N={N}, d={d} + {n_predict} predict(x) calls, unmodified "
+                    "exauq from baseline/_ref on the restated mogp; one LOO refit of the reference's loop "
+                    "(exauq/core/designers.py:263-272) costs one such fit + one predict",
+            "fit_s": fit_s, "predict_s_per_call": pred_s,
+            "loo_sweep_s_extrapolated": N * (fit_s + pred_s)}
 
 
 def use_all_host_threads():
@@ -185,27 +231,30 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import gp_oracle as orc
+    from exauq_toolbox_b200.workload import synthetic_candidates, synthetic_problem
 
     use_all_host_threads()
-    X, y = orc.synthetic_problem(a.n_train, a.dim)
-    Xc = orc.synthetic_candidates(4096, a.dim)
+    X, y = synthetic_problem(a.n_train, a.dim)        # the same arrays the B200 arm uses
+    Xc = synthetic_candidates(4096, a.dim)
+    n_gpus = max(1, a.gpus)
     vals, times = [], []
     for s in range(a.warmup + a.steps):
         t0 = time.perf_counter()
-        v, parts, sample = cpu_port_sample(a, X, y, Xc)
+        v, parts, sample = cpu_port_sample(a, X, y, Xc, n_gpus=n_gpus)
         if s >= a.warmup:
             vals.append(v)
             times.append(time.perf_counter() - t0)
     value = float(np.mean(vals))
     cores = host_threads()
+    stock = stock_path_sample(a) if not a.no_stock_path else {"skipped": "--no-stock-path"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * a.candidates / value, "sample_ms_per_step": 1e3 * float(np.mean(times)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, 1),
+        "warmup": a.warmup, "ms_per_step": 1e3 * a.candidates * n_gpus / value,
+        "sample_ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, n_gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "parts": parts},
+                         "parts": parts, "stock_path": stock},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -237,14 +286,11 @@ def run_b200(a):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         comm = TorchComm(device=torch.device("cuda", local))
 
-    from scipy.stats.qmc import LatinHypercube
+    from exauq_toolbox_b200.workload import synthetic_candidates, synthetic_problem
 
     N, d, M = a.n_train, a.dim, a.candidates
-    k = np.arange(1, d + 1)
-    X = LatinHypercube(d, seed=1).random(N)
-    # three periods per coordinate: keeps the PEI product from underflowing to 0 at N=4096
-    y = np.sum(np.sin(6 * np.pi * X) / k, axis=1) + X[:, 0] * X[:, 1 % d] - math.sqrt(2.0)
-    Xc = LatinHypercube(d, seed=2 + rank).random(M)
+    X, y = synthetic_problem(N, d)                    # the same arrays the reference arm uses
+    Xc = synthetic_candidates(M, d, seed=2 + rank)
     if torch is not None:
         pinned = torch.from_numpy(Xc).pin_memory()
         Xc = pinned.numpy()
@@ -329,6 +375,40 @@ def run_b200(a):
     e2e = {"value": world * M / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    # ---- north-star strong scaling: ONE design batch (--candidates and --restarts in TOTAL) split over the ranks ----
+    # candidates: M / world per rank; restarts: the same 15 starting points whatever the world size, owned round-robin
+    # (design.fit_errors_gp restart_split="global"), every round's evaluations shared evenly over the ranks
+    strong = None
+    if world > 1 and a.scaling == "weak" and a.strong_steps > 0:
+        Ms = (M + world - 1) // world
+        res_s = exq.DeviceCandidates(Xc[:Ms])
+        sstats = {}
+
+        def strong_step():
+            sstats.clear()
+            return design_batch(X, y, "Matern52", ell, cov, nug, bounds, res_s, batch_size=a.batch_size,
+                                n_tries=a.restarts, seed=12345, comm=comm, candidate_offset=rank * Ms, stats=sstats,
+                                restart_split="global")
+
+        for _ in range(2):
+            strong_step()
+        sync_barrier()
+        _lib.timer_start()
+        for _ in range(a.strong_steps):
+            sout = strong_step()
+        sms = _lib.timer_stop()
+        comm.barrier()
+        sms = float(np.max(comm.allgather(np.array([sms])))) / a.strong_steps
+        strong = {"design_batch_s": sms * 1e-3, "candidates_total": Ms * world, "restarts_total": a.restarts,
+                  "n_gpus": world, "steps": a.strong_steps, "value": Ms * world / (sms * 1e-3), "unit": UNIT,
+                  "map_evals_total": int(np.sum(comm.allgather(np.array([float(sstats.get("map_evals", 0))])))),
+                  "map_rounds": sstats.get("map_batches"), "map_s": sstats.get("map_s"), "pei_s": sstats.get("pei_s"),
+                  "loo_s": sstats.get("loo_s"), "map_comm_s": sstats.get("map_comm_s"),
+                  "selected_indices": [int(i) for i in sout[1]],
+                  "note": "one batch of --candidates candidates and --restarts restarts in total, split over the ranks; "
+                          "same 15 starting points as the 1-GPU run (restart_split=global)"}
+        res_s.close()
+
     if rank != 0:
         return
 
@@ -363,13 +443,24 @@ def run_b200(a):
     vk = kern[vname]
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    # kind::i8 issues at twice the kind::f16 rate on the same pipe; MEASURED_PEAKS.json has no int8 entry, so the
-    # denominator is 2 x the measured bf16 burst figure (the int8 kernels run in bursts of a few ms between
-    # FP64-pipe and memory-bound kernels and hold 1965 MHz; 2 x the power-capped sustained figure, 2860, is
-    # exceeded by the variance kernel).  Nominal dense int8: 4500 TOP/s.
-    i8_peak = 2.0 * peaks.get("bf16_tflops", 1703.4)
-    i8_src = ("2 x MEASURED_PEAKS.json bf16_tflops (burst; kind::i8 issues at twice the kind::f16 rate on the same pipe; "
-              "no measured int8 entry; nominal 4500)")
+    # int8 roofline denominator: MEASURED on this pool's B200 by tools/micro/umma_i8_peak.cu (profiles/int8_peak_r02.json):
+    # tcgen05.mma.kind::i8 issued back to back from resident shared-memory tiles, M=128, N=64/128/256.  These kernels
+    # are timed inside a long step, so the SUSTAINED figure (2 s back to back; the best N) is the denominator; the burst
+    # figure, 2 x the measured bf16 burst (round 1's assumed denominator) and the nominal 4500 are printed beside it.
+    i8_burst, i8_sust, i8_src = None, None, None
+    ipath = os.path.join(ROOT, "profiles", "int8_peak_r02.json")
+    if os.path.exists(ipath):
+        ip = json.load(open(ipath))["umma_i8_issue_loop_tops"]
+        i8_burst = max(v["burst"] for v in ip.values())
+        i8_sust = max(v["sustained"] for v in ip.values())
+        i8_src = ("measured: profiles/int8_peak_r02.json (tools/micro/umma_i8_peak.cu, UTCIMMA issue loop M=128 N=64..256 "
+                  "from resident smem tiles), sustained figure because the kernel is timed inside a long step")
+    i8_assumed = 2.0 * peaks.get("bf16_tflops", 1703.4)
+    i8_peak = i8_sust if i8_sust else i8_assumed
+    if not i8_src:
+        i8_src = "fallback: 2 x MEASURED_PEAKS.json bf16_tflops (no measured int8 file found)"
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+    ncu_traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 
     def add_int8(entry, p, digits):
         # The pipe these kernels run on is the int8 tensor core, so the roofline is int8 operations issued against
@@ -379,10 +470,21 @@ def run_b200(a):
         entry.update(fp64_equivalent_tflops=entry["achieved"], fp64_dmma_peak_tflops=fp64_peak,
                      fp64_equivalent_over_dmma_peak=entry["achieved"] / fp64_peak,
                      achieved=i8, peak=i8_peak, frac=i8 / i8_peak, unit="TOP/s", peak_source=i8_src,
+                     frac_of_measured_burst=(i8 / i8_burst) if i8_burst else None, peak_measured_burst=i8_burst,
+                     frac_of_2x_bf16_burst=i8 / i8_assumed, frac_of_nominal_4500=i8 / 4500.0,
+                     int8_ops_counted="issued: the kernel's own tile walk x digit products (exq_int8_gemm_ops; "
+                                      "tests/test_roofline_accounting.py)",
                      products_per_fp64_product=digits * (digits + 1) // 2)
 
     if kern[fname] is not None:
         add_int8(kern[fname], prof["gemm_factor_i8"], fslices)
+        t = ncu_traffic.get("oz::gemm_kernel")
+        if t and (N, d) == (4096, 8):
+            # per-launch DRAM bytes from `ncu --set full` captures of the shipped kernel (launch-weighted mean over the
+            # captured node shapes) with the algorithmic plane bytes of the same launches beside them
+            kern[fname]["traffic"] = t.get("dram_bytes_per_launch")
+            kern[fname]["algorithmic_bytes"] = t.get("algorithmic_bytes_per_launch")
+            kern[fname]["traffic_source"] = t.get("source")
     if vk is not None and slices:
         add_int8(vk, prof["gemm_predict"], slices)
         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel (profiles/ncu_summary_r01.md,
@@ -418,12 +520,12 @@ def run_b200(a):
         "phases_s": {k: stats.get(k) for k in ("loo_s", "map_s", "map_gpu_s", "pei_s", "map_allgather_wait_s",
                                                 "pei_eval_call_s", "pei_argmax_s", "pei_allgather_s", "pei_add_point_s")},
         "selected_indices": [int(i) for i in out[1]],
+        "strong": strong,
+        "guard": dict(zip(("widened", "fallbacks"), _lib.guard_counts())),
     }
     if world == 1 and not a.no_cpu_baseline:
-        from oracle import gp_oracle as orc  # checker / CPU baseline leg only
-
         use_all_host_threads()
-        v, parts, sample = cpu_port_sample(a, X, y, orc.synthetic_candidates(4096, d))
+        v, parts, sample = cpu_port_sample(a, X, y, synthetic_candidates(4096, d), map_evals=map_evals)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample,
                                 "parts": parts}
     else:

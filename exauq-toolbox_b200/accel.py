@@ -1,0 +1,121 @@
+"""Host-side drop-ins that let the reference's UNCHANGED designers run at benchmark size (SURVEY.md section 8f items
+1 and 2; VERDICT r01 "missing" 3 and 4).  Nothing here edits the reference: ``FastSimulatorDomain`` is a subclass
+of ``exauq.core.modelling.SimulatorDomain`` that a caller passes where a domain is expected, and
+``accelerate_designers()`` is an opt-in context manager that swaps the ``maximise`` the designers call for one that
+evaluates whole differential-evolution populations on the device.
+
+Why they are needed (the GPU batch itself is ~0.7 s at N = 4096, d = 8):
+
+* ``SimulatorDomain.calculate_pseudopoints`` (exauq/core/modelling.py:2233-2277 via ``closest_boundary_points``
+  :2157-2231) is a pure-Python loop over 2 d faces x N inputs with an ``Input in corners`` scan (2^d comparisons)
+  for every one of them -- O(2 d N 2^d), ~88 s at N = 4096, d = 8; ``_define_corners`` (:2142-2151) is O(4^d).
+* ``maximise`` (exauq/utilities/optimisation.py:14-104) drives scipy's differential evolution with a scalar
+  objective: every population member costs one ``predict`` + one ``covariance_matrix`` round trip to the device.
+"""
+
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import numpy as np
+
+from .design import domain_corners, maximise_pei_de, pseudopoints
+from .gp import B200GaussianProcess, inputs_to_array
+from .refapi import Input, SimulatorDomain  # the reference classes being specialised
+
+
+class FastSimulatorDomain(SimulatorDomain):
+    """``SimulatorDomain`` with vectorised corner and pseudopoint computations.  Same results (same points, same
+    order, same error behaviour) as the reference methods it overrides; tests/test_host_logic.py compares them."""
+
+    def _define_corners(self):
+        """exauq/core/modelling.py:2142-2151 in O(2^d): the product of the bounds, duplicates (degenerate sides) dropped."""
+        self._corners = tuple(Input(*c) for c in domain_corners(self._bounds))
+        self._lo = np.array([b[0] for b in self._bounds], dtype=float)
+        self._hi = np.array([b[1] for b in self._bounds], dtype=float)
+
+    def _as_array(self, inputs) -> np.ndarray:
+        self._validate_points_dim(inputs)                       # same ValueError as the reference
+        X = inputs_to_array(inputs) if len(inputs) else np.empty((0, self._dim))
+        if X.shape[0] and not (np.all(X >= self._lo) and np.all(X <= self._hi)):
+            # the reference tests membership with `point in self` (bounds inclusive): defer to it for the message
+            if not all(point in self for point in inputs):
+                raise ValueError("All points in the collection must be within the domain bounds.")
+        return X
+
+    def closest_boundary_points(self, inputs):
+        """exauq/core/modelling.py:2157-2231, vectorised (``design.pseudopoints`` minus the corners)."""
+        if not inputs:
+            return tuple()
+        X = self._as_array(inputs)
+        pts = pseudopoints(X, self._bounds)
+        n_corners = len(self._corners)
+        boundary = pts[: pts.shape[0] - n_corners] if n_corners else pts
+        return tuple(Input(*p) for p in boundary)
+
+    def calculate_pseudopoints(self, inputs):
+        """exauq/core/modelling.py:2233-2277: boundary pseudopoints followed by the corners, no duplicates."""
+        if not inputs:
+            return tuple(self._corners)
+        X = self._as_array(inputs)
+        return tuple(Input(*p) for p in pseudopoints(X, self._bounds))
+
+
+def _find_pei_calculator(func):
+    """The ``PEICalculator`` a designer's objective closes over (``lambda x: pei.compute(x)``,
+    exauq/core/designers.py:830-832 and :1361), or None."""
+    cells = getattr(func, "__closure__", None) or ()
+    for cell in cells:
+        try:
+            obj = cell.cell_contents
+        except ValueError:
+            continue
+        if all(hasattr(obj, a) for a in ("_gp", "_other_repulsion_points", "_max_targets", "compute")):
+            return obj
+    owner = getattr(func, "__self__", None)                    # a bound method pei.compute passed directly
+    if owner is not None and all(hasattr(owner, a) for a in ("_gp", "_other_repulsion_points", "_max_targets")):
+        return owner
+    return None
+
+
+def batched_maximise(func, domain, seed: Optional[int] = None, _fallback=None):
+    """Signature and return value of ``exauq.utilities.optimisation.maximise``.  When ``func`` is the
+    pseudo-expected improvement of a ``B200GaussianProcess`` (a closure over a ``PEICalculator``), the same
+    optimiser -- scipy differential evolution, ``tol = atol = 1e-9``, bounds of the domain, same seed -- runs
+    with every generation's population evaluated in ONE device call (``design.maximise_pei_de``: ``vectorized=True``
+    needs ``updating='deferred'``, so the iterates are not those of the scalar run; the maximum found agrees within
+    the optimiser's tolerance).  Anything else goes to the reference's ``maximise`` unchanged."""
+    if _fallback is None:
+        from exauq.utilities.optimisation import maximise as _fallback
+    if not isinstance(domain, SimulatorDomain):
+        return _fallback(func, domain, seed=seed)              # raises the reference's TypeError
+    pei = _find_pei_calculator(func)
+    gp = getattr(pei, "_gp", None)
+    if pei is None or not isinstance(gp, B200GaussianProcess) or not gp.training_data:
+        return _fallback(func, domain, seed=seed)
+    if seed is not None and not isinstance(seed, int):
+        raise TypeError(f"Expected 'seed' to be of type int, but received {type(seed)} instead.")
+    rep = pei._other_repulsion_points
+    rep_arr = inputs_to_array(rep) if len(rep) else np.empty((0, domain.dim))
+    dev = gp._real_state().dev
+    x, val = maximise_pei_de(dev, [tuple(b) for b in domain.bounds], rep_arr, float(pei._max_targets), seed=seed)
+    return Input(*x), float(val)
+
+
+@contextlib.contextmanager
+def accelerate_designers():
+    """Inside the ``with`` block ``exauq.core.designers`` maximises pseudo-expected improvements of B200 GPs through
+    ``batched_maximise``; every other call behaves as before.  The module attribute is restored on exit."""
+    import exauq.core.designers as designers
+
+    original = designers.maximise
+
+    def patched(func, domain, seed=None):
+        return batched_maximise(func, domain, seed=seed, _fallback=original)
+
+    designers.maximise = patched
+    try:
+        yield
+    finally:
+        designers.maximise = original

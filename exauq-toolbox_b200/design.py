@@ -426,22 +426,26 @@ def multi_level_design_batch(
     gp_factory=DeviceGP,
     cand_factory=DeviceCandidates,
     stats: Optional[dict] = None,
+    restart_split: str = "per_rank",
+    return_details: bool = False,
 ):
     """compute_multi_level_loo_samples (designers.py:1184-1378) over a fixed candidate set:
     per-level errors GPs fitted to the multi-level LOO errors, then ``batch_size`` rounds of
     [arg max over candidates of PEI_l / cost_l for every level, take the best level, add the
-    point to THAT level's repulsion set].  Returns a list of (level, global index, point, value)."""
+    point to THAT level's repulsion set].  Returns a list of (level, global index, point, value)
+    (``return_details``: also ``{level: errors-GP raw theta}`` and ``{level: NES errors}``)."""
     comm = comm or SingleComm()
     stats = stats if stats is not None else {}
     nes, _ = multi_level_loo_errors(levels, coefficients, gp_factory)
     Xc = candidates.Xc if hasattr(candidates, "Xc") else np.ascontiguousarray(candidates, dtype=float)
-    gp_e, cands = {}, {}
+    gp_e, cands, thetas = {}, {}, {}
     for lv in sorted(levels):
         X = np.ascontiguousarray(levels[lv]["X"], dtype=float)
         if not np.all(np.isfinite(nes[lv])):
             raise FloatingPointError(f"non-finite NES error at level {lv}")
         lvl_seed = None if seed is None else seed + 104729 * lv
-        gp_e[lv], _ = fit_errors_gp(X, nes[lv], levels[lv]["kernel"], bounds, n_tries, lvl_seed, comm, gp_factory, stats)
+        gp_e[lv], thetas[lv] = fit_errors_gp(X, nes[lv], levels[lv]["kernel"], bounds, n_tries, lvl_seed, comm, gp_factory,
+                                             stats, restart_split)
         cands[lv] = cand_factory(Xc)
         cands[lv].pei_eval(gp_e[lv], pseudopoints(X, bounds), float(np.max(nes[lv])))
     chosen = []
@@ -453,4 +457,6 @@ def multi_level_design_batch(
                 best = (lv, gi, pt, v)
         chosen.append(best)
         cands[best[0]].add_point(gp_e[best[0]], best[2])
+    if return_details:
+        return chosen, thetas, nes
     return chosen

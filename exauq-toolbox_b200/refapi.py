@@ -31,3 +31,4 @@ GaussianProcessHyperparameters = _m.GaussianProcessHyperparameters
 GaussianProcessPrediction = _m.GaussianProcessPrediction
 Input = _m.Input
 TrainingDatum = _m.TrainingDatum
+SimulatorDomain = _m.SimulatorDomain

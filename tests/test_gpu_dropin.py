@@ -392,3 +392,56 @@ def test_csv_in_design_points_out(api, tmp_path):
     for lv in ref.levels:
         for a, b in zip(ours[lv], ref[lv]):
             assert np.allclose(np.array(a), np.array(b), atol=5e-3)
+
+
+def test_unchanged_single_level_designer_with_fast_domain_and_batched_de(api):
+    """The reference's compute_single_level_loo_samples, UNCHANGED, given a FastSimulatorDomain and run inside
+    accelerate_designers() (differential-evolution populations evaluated per generation on the device): same new
+    design point as the golden run of the reference's scalar path on config 1 (tests/golden/slas_config1.json),
+    within the tolerance the scalar path itself is held to."""
+    from exauq_toolbox_b200 import _lib
+    from exauq_toolbox_b200.accel import FastSimulatorDomain, accelerate_designers
+
+    g = load_golden("slas_config1.json")
+    domain = FastSimulatorDomain([tuple(b) for b in g["domain"]])
+    data = _data(api, g)
+    np.random.seed(g["gp_fit_seed"])
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data)
+    np.random.seed(g["errors_gp_fit_seed"])
+    n0 = _lib.launch_count()
+    with accelerate_designers():
+        new = api.designers.compute_single_level_loo_samples(gp, domain, batch_size=1, seed=g["de_seed"])
+    assert np.allclose(np.array(new[0]), g["new_design_point"], atol=2e-3)
+    assert new[0] in domain
+    assert _lib.launch_count() > n0
+    # a batch of 3: distinct points, all inside the domain, the first one as before
+    np.random.seed(g["errors_gp_fit_seed"])
+    with accelerate_designers():
+        batch = api.designers.compute_single_level_loo_samples(gp, domain, batch_size=3, seed=g["de_seed"])
+    assert len(batch) == 3 and all(x in domain for x in batch)
+    assert len({tuple(np.round(np.array(x), 6)) for x in batch}) == 3
+
+
+def test_batched_de_pei_equals_peicalculator_at_the_optimum(api):
+    """batched_maximise returns (x, PEI(x)) like maximise: the value must be the reference PEICalculator's own
+    value at that point, and no worse than what the reference's scalar maximise finds."""
+    from exauq_toolbox_b200.accel import FastSimulatorDomain, batched_maximise
+
+    g = load_golden("fixed_matern_d3_n40.json")
+    data = _data(api, g)
+    hp = g["hyperparameters"]
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters(hp["corr_length_scales"], hp["process_var"],
+                                                                   hp["nugget"]))
+    lo = np.min(np.array(g["X"]), axis=0) - 0.05
+    hi = np.max(np.array(g["X"]), axis=0) + 0.05
+    domain = FastSimulatorDomain([(float(a), float(b)) for a, b in zip(lo, hi)])
+    pei = api.designers.PEICalculator(domain, gp)
+    x, val = batched_maximise(lambda x: pei.compute(x), domain, seed=7)
+    assert x in domain
+    assert close(val, pei.compute(x), rel=1e-7, abs_=1e-12)
+    from exauq.utilities.optimisation import maximise
+
+    xs, vs = maximise(lambda x: pei.compute(x), domain, seed=7)
+    assert val >= vs * (1 - 1e-6)

@@ -369,3 +369,76 @@ def test_committed_bench_lines_follow_the_contract():
     ref = json.load(open(os.path.join(root, "profiles", "bench_r01_reference_arm.json")))
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_bench_workload_is_the_oracles_workload():
+    """bench.py's two arms share exauq_toolbox_b200.workload; the oracle keeps its own copy for the tests -- same arrays."""
+    import exauq_toolbox_b200.workload as w
+    from oracle import gp_oracle as orc
+
+    Xa, ya = w.synthetic_problem(64, 5)
+    Xb, yb = orc.synthetic_problem(64, 5)
+    assert np.array_equal(Xa, Xb) and np.array_equal(ya, yb)
+    assert np.array_equal(w.synthetic_candidates(100, 5, seed=7), orc.synthetic_candidates(100, 5, seed=7))
+
+
+@needs_exauq
+def test_fast_simulator_domain_equals_the_reference_domain():
+    """FastSimulatorDomain (vectorised corners / pseudopoints) against exauq's SimulatorDomain: same points in the
+    same order, same errors, usable wherever a SimulatorDomain is expected (isinstance, deepcopy, scale, in)."""
+    import copy
+
+    from exauq.core.modelling import Input, SimulatorDomain
+
+    from exauq_toolbox_b200.accel import FastSimulatorDomain
+
+    rng = np.random.default_rng(0)
+    for bounds in ([(0, 1), (0, 1)], [(-1, 2), (0, 0.5), (3, 4)], [(0, 1), (2, 2), (0, 1)], [(0, 1)] * 5):
+        ref, fast = SimulatorDomain(bounds), FastSimulatorDomain(bounds)
+        assert isinstance(fast, SimulatorDomain) and fast.dim == ref.dim and fast.bounds == ref.bounds
+        assert fast.corners == ref.corners
+        d = len(bounds)
+        lo = np.array([b[0] for b in bounds], float)
+        hi = np.array([b[1] for b in bounds], float)
+        X = lo + rng.uniform(0, 1, (40, d)) * (hi - lo)
+        X[3] = lo                                             # a corner among the inputs
+        X[7, 0] = hi[0]                                       # an input on a face
+        X[9] = X[8]                                           # duplicates
+        inputs = [Input(*row) for row in X]
+        assert fast.calculate_pseudopoints(inputs) == ref.calculate_pseudopoints(inputs)
+        assert fast.closest_boundary_points(inputs) == ref.closest_boundary_points(inputs)
+        assert fast.calculate_pseudopoints([]) == ref.calculate_pseudopoints([])
+        assert fast.closest_boundary_points([ref.corners[0]]) == ref.closest_boundary_points([ref.corners[0]])
+        c = copy.deepcopy(fast)
+        assert c.calculate_pseudopoints(inputs) == ref.calculate_pseudopoints(inputs)
+        assert (Input(*X[0]) in fast) and fast.scale([0.5] * d) == ref.scale([0.5] * d)
+        outside = [Input(*(hi + 1.0))]
+        for dom in (ref, fast):
+            with pytest.raises(ValueError, match="within the domain bounds"):
+                dom.calculate_pseudopoints(outside)
+            with pytest.raises(ValueError, match="same dimensionality"):
+                dom.calculate_pseudopoints([Input(*([0.5] * (d + 1)))])
+
+
+@needs_exauq
+def test_batched_maximise_falls_back_for_foreign_objectives():
+    """accelerate_designers(): objectives that are not the PEI of a B200 GP reach the reference's maximise
+    unchanged (same optimum, same seed), and the module attribute is restored afterwards."""
+    import exauq.core.designers as designers
+    from exauq.core.modelling import SimulatorDomain
+    from exauq.utilities.optimisation import maximise
+
+    from exauq_toolbox_b200.accel import accelerate_designers, batched_maximise
+
+    dom = SimulatorDomain([(0, 1), (0, 1)])
+    f = lambda x: -((x[0] - 0.3) ** 2 + (x[1] - 0.6) ** 2)  # noqa: E731
+    a = maximise(f, dom, seed=3)
+    b = batched_maximise(f, dom, seed=3)
+    assert a[0] == b[0] and a[1] == b[1]
+    before = designers.maximise
+    with accelerate_designers():
+        assert designers.maximise is not before
+        c = designers.maximise(f, dom, seed=3)
+    assert designers.maximise is before and c[0] == a[0]
+    with pytest.raises(TypeError):
+        batched_maximise(f, "not a domain")
