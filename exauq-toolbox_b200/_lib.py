@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("EXQ_LIB", os.path.join(_HERE, "libexauq_b200.so"))  #
 EXQ_OK, EXQ_ERR_ARG, EXQ_ERR_CUDA, EXQ_ERR_STATE, EXQ_NOT_PD = 0, -1, -2, -3, 1
 KERNEL_IDS = {"Matern52": 0, "SquaredExponential": 1, "ProductMat52": 2}
 NUGGET_FIXED, NUGGET_ADAPTIVE, NUGGET_FIT = 0, 1, 2
-PROF_GEMM_PREDICT, PROF_GEMM_FACTOR, PROF_LEAF, PROF_ASSEMBLE, PROF_STREAM, PROF_GEMM_FACTOR_I8, PROF_SLICE = range(7)
+PROF_GEMM_PREDICT, PROF_GEMM_FACTOR, PROF_LEAF, PROF_ASSEMBLE, PROF_STREAM, PROF_GEMM_FACTOR_I8, PROF_SLICE, PROF_FUSED = range(8)
 
 # every symbol include/exauq_b200.h declares: (name, restype, argtypes)
 _dp = C.POINTER(C.c_double)
@@ -37,6 +37,8 @@ SIGNATURES = {
     "exq_set_guard": (C.c_int, [C.c_double, C.c_double]),
     "exq_guard_counts": (C.c_int, [_lp, _lp]),
     "exq_set_refine_steps": (C.c_int, [C.c_int]),
+    "exq_set_fused": (C.c_int, [C.c_int, C.c_int]),
+    "exq_fused_info": (C.c_int, [_ip, _ip, _ip]),
     "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
     "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "exq_timer_start": (C.c_int, []),
@@ -354,6 +356,19 @@ def set_guard(widen: float = 2.0 ** 16, fallback: float = 1e12) -> None:
     """Thresholds of the conditioning guard of the int8 paths (see include/exauq_b200.h)."""
     init()
     check(load().exq_set_guard(float(widen), float(fallback)), "exq_set_guard")
+
+
+def set_fused(max_rows: int = 512, cluster_ctas: int = 0) -> None:
+    """Fused sub-tree kernel: largest diagonal block handled by one launch (0 = off) and CTAs per cluster (0 = automatic)."""
+    init()
+    check(load().exq_set_fused(int(max_rows), int(cluster_ctas)), "exq_set_fused")
+
+
+def fused_info() -> dict:
+    init()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(load().exq_fused_info(C.byref(a), C.byref(b), C.byref(c)), "exq_fused_info")
+    return {"max_rows": a.value, "clusters_of_8": b.value, "clusters_of_16": c.value}
 
 
 def set_refine_steps(steps: int = 1) -> None:

@@ -18,6 +18,7 @@
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
 #include "leaf.cuh"
+#include "fused_node.cuh"
 #include "ozaki_i8.cuh"
 #include "ozaki_gemm.cuh"
 
@@ -77,6 +78,13 @@ struct Ctx {
     double guard_widen = 65536.0;          // 2^16   (EXQ_GUARD_WIDEN)
     double guard_fallback = 1.0e12;        //        (EXQ_GUARD_FALLBACK)
     bool oz_off = false;                   // set while a guarded system is re-evaluated on FP64 DMMA
+    // fused sub-tree kernel (fused_node.cuh): diagonal blocks of up to fuse_n rows are factored + inverted by ONE launch
+    // (a cluster of fuse_g CTAs per system); 0 switches it off (EXQ_FUSE_N / EXQ_FUSE_G; fuse_g = 0: 16 CTAs for up to 8
+    // systems, 8 otherwise)
+    int fuse_n = 512;
+    int fuse_g = 0;
+    bool fuse_np16 = false;                // non-portable cluster size 16 accepted by the driver
+    int fuse_clusters16 = 0, fuse_clusters8 = 0;   // co-resident clusters of 16 / 8 CTAs (cudaOccupancyMaxActiveClusters)
     int refine_steps = 1;                  // iterative-refinement steps of alpha after an int8 factorisation (EXQ_REFINE_STEPS)
     int64_t guard_widened = 0, guard_fallbacks = 0;
 } g;
@@ -157,6 +165,29 @@ int set_kernel_attrs() {
 #undef EXQ_SET_GEMM_ATTR
     CUDA_TRY(cudaFuncSetAttribute(leaf_potrf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   LEAF_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(fused_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES));
+    g.fuse_np16 = cudaFuncSetAttribute(fused_factor_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+    {   // can the device co-schedule the clusters at all?  (16 CTAs need 16 free SMs inside one GPC)
+        auto clusters = [&](int G) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G, 1, 1);
+            cfg.blockDim = dim3(FUSED_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = FUSED_SMEM_BYTES;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, fused_factor_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            return n;
+        };
+        g.fuse_clusters16 = g.fuse_np16 ? clusters(16) : 0;
+        g.fuse_clusters8 = clusters(8);
+        if (g.fuse_clusters16 < 1) g.fuse_np16 = false;
+        if (g.fuse_clusters8 < 1) g.fuse_n = 0;   // no clusters on this device: one launch per step, as before
+    }
     CUDA_TRY(oz::set_attrs<5>());
     CUDA_TRY(oz::set_attrs<6>());
     CUDA_TRY(oz::set_attrs<7>());
@@ -468,9 +499,37 @@ int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int 
     return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
 }
 
+// potrf + trtri of the diagonal block [r0, r0+n) of every system in s by ONE launch of fused_factor_kernel
+int launch_fused(Sys& s, int r0, int n) {
+    FusedArgs a{};
+    a.A = s.A; a.Linv = s.Linv; a.ld = s.Np; a.stride = s.sq(); a.info = s.info;
+    int G = g.fuse_g;
+    if (G <= 0) G = (g.fuse_np16 && s.B <= g.fuse_clusters16) ? 16 : 8;
+    if (G > 8 && !g.fuse_np16) G = 8;
+    a.n_ops = 0;
+    if (!fused_build(a.ops, a.n_ops, r0, n, G)) return fail(EXQ_ERR_STATE, "fused sub-tree: step list overflow");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G, s.B, 1);
+    cfg.blockDim = dim3(FUSED_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = FUSED_SMEM_BYTES;
+    cfg.stream = g.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // potrf + trtri of an n x n block: 2/3 n^3 flop
+    ProfMark m = prof_begin(EXQ_PROF_FUSED, s.B * (2.0 / 3.0) * (double)n * n * n, 0.0);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fused_factor_kernel, a);
+    prof_end(m);
+    if (e != cudaSuccess) return fail(EXQ_ERR_CUDA, std::string("fused_factor_kernel: ") + cudaGetErrorString(e));
+    return check_launch("fused_factor_kernel");
+}
+
 // fused recursive potrf + trtri on the diagonal block [r0, r0+n) of every system in s
 int factor_rec(Sys& s, int r0, int n) {
     const int64_t ld = s.Np, sq = s.sq();
+    if (n > 128 && n <= g.fuse_n) return launch_fused(s, r0, n);
     if (n == 128) {
         ProfMark m = prof_begin(EXQ_PROF_LEAF, s.B * (128.0 * 128 * 128), 0.0);
         leaf_potrf_trtri_kernel<<<s.B, LEAF_THREADS, LEAF_SMEM_BYTES, g.stream>>>(s.A, s.Linv, ld, sq, sq, r0,
@@ -610,7 +669,7 @@ int assemble_sym(Sys& s, const double* X, int64_t strideX, int nvalid, int kerne
 }
 
 int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
-    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 64) * want_chunk;
+    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 32) * want_chunk;   // int8: 2 partials per 64 rows
     if (g.kct_elems < need_k) {
         cudaFree(g.KcT);
         g.KcT = nullptr; g.kct_elems = 0;
@@ -760,7 +819,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
         if ((rc = launch_gemm<LAYOUT_K, LAYOUT_K>(ga, 1, EXQ_PROF_GEMM_PREDICT))) return rc;
         }
         FinArgs f{};
-        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : (use_oz ? Np / oz::BLK_R : Np / g.variance_bm);
+        f.KcT = gp->KcT; f.ld = Np; f.P = gp->P; f.ldp = mc_pad; f.nrb = (mc <= 8) ? 1 : (use_oz ? 2 * (Np / oz::BLK_R) : Np / g.variance_bm);
         f.alpha = gp->fit.alpha; f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep;
         f.N = (int)gp->N; f.Np = Np; f.d = gp->d; f.kernel_id = gp->kernel_id; f.m_valid = (int)mc;
         f.tmax = tmax; f.want_pei = want_pei;
@@ -931,6 +990,8 @@ int exq_init(int device) {
     }
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_FUSE_N")) { const int v = atoi(e); g.fuse_n = (v >= 256 && v <= 1024) ? (v / 128) * 128 : 0; }
+    if (const char* e = getenv("EXQ_FUSE_G")) { const int v = atoi(e); g.fuse_g = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : 0; }
     if (const char* e = getenv("EXQ_REFINE_STEPS")) g.refine_steps = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("EXQ_GUARD_WIDEN")) g.guard_widen = std::max(1.0, atof(e));
     if (const char* e = getenv("EXQ_GUARD_FALLBACK")) g.guard_fallback = std::max(g.guard_widen, atof(e));
@@ -966,6 +1027,13 @@ int exq_shutdown(void) {
 }
 
 int exq_device_sm_count(void) { return g.sm_count; }
+int exq_fused_info(int* max_rows, int* clusters8, int* clusters16) {
+    REQUIRE_READY();
+    if (max_rows) *max_rows = g.fuse_n;
+    if (clusters8) *clusters8 = g.fuse_clusters8;
+    if (clusters16) *clusters16 = g.fuse_clusters16;
+    return EXQ_OK;
+}
 int exq_variance_slices(void) { return g.oz_slices; }
 int exq_factor_slices(void) { return g.oz_factor_slices; }
 int exq_set_int8_digits(int variance_digits, int factor_digits) {
@@ -988,6 +1056,17 @@ int exq_set_guard(double widen, double fallback) {
     if (!(widen >= 1.0) || !(fallback >= widen)) return fail(EXQ_ERR_ARG, "exq_set_guard: need 1 <= widen <= fallback");
     g.guard_widen = widen;
     g.guard_fallback = fallback;
+    return EXQ_OK;
+}
+int exq_set_fused(int max_rows, int cluster_ctas) {
+    REQUIRE_READY();
+    if (!(max_rows == 0 || (max_rows >= 256 && max_rows <= 1024 && max_rows % 128 == 0)))
+        return fail(EXQ_ERR_ARG, "exq_set_fused: max_rows must be 0 or a multiple of 128 in [256, 1024]");
+    if (!(cluster_ctas == 0 || cluster_ctas == 1 || cluster_ctas == 2 || cluster_ctas == 4 || cluster_ctas == 8 ||
+          cluster_ctas == 16))
+        return fail(EXQ_ERR_ARG, "exq_set_fused: cluster_ctas must be 0 (automatic), 1, 2, 4, 8 or 16");
+    g.fuse_n = max_rows;
+    g.fuse_g = cluster_ctas;
     return EXQ_OK;
 }
 int exq_set_refine_steps(int steps) {

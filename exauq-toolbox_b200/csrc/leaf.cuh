@@ -30,12 +30,12 @@ constexpr int LEAF_SMEM_DOUBLES =
     LEAF_N * LEAF_LD + LEAF_NBLK * 8 * LEAF_XD_LD + LEAF_N + 8 * 8 * LEAF_XD_LD;
 constexpr int LEAF_SMEM_BYTES = LEAF_SMEM_DOUBLES * (int)sizeof(double);
 
-// A, Linv: pointers to the (row-major, leading dimension ld) full matrices of batch 0;
-// the leaf works on rows/cols [r0, r0+128).  info[batch] receives first bad column + 1.
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall, int64_t ld,
-                        int64_t strideA, int64_t strideL, int r0, int* __restrict__ info) {
-    extern __shared__ __align__(16) double leaf_smem[];
+// The leaf proper: A and Li point at the 128 x 128 diagonal block (leading dimension ld) of one system,
+// *info_sys receives (first bad column + 1 + info_base), leaf_smem is LEAF_SMEM_BYTES of shared memory.
+// Called by the stand-alone kernel below and, for CTA 0 of a cluster, by fused_factor_kernel (fused_node.cuh), where
+// the block was last written by other CTAs: its global reads bypass L1 (ld.global.cg).
+__device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __restrict__ Li, int64_t ld,
+                                          int* __restrict__ info_sys, int info_base, double* leaf_smem) {
     double* S = leaf_smem;
     double* XD = S + LEAF_N * LEAF_LD;                 // [16][8][12]
     double* rinv = XD + LEAF_NBLK * 8 * LEAF_XD_LD;    // [128]
@@ -43,8 +43,6 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    double* A = Aall + (int64_t)blockIdx.x * strideA + (int64_t)r0 * ld + r0;
-    double* Li = Linvall + (int64_t)blockIdx.x * strideL + (int64_t)r0 * ld + r0;
 
 #ifdef EXQ_LEAF_PROFILE
     long long t_prev = clock64();
@@ -62,7 +60,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
         c[s][0] = c[s][1] = 0.0;
         if (tb[s] >= 0) {
             int row = 8 * bi + g, col = 8 * bj + 2 * t;
-            double2 v = *reinterpret_cast<const double2*>(A + (int64_t)row * ld + col);
+            double2 v = __ldcg(reinterpret_cast<const double2*>(A + (int64_t)row * ld + col));
             c[s][0] = (col <= row) ? v.x : 0.0;
             c[s][1] = (col + 1 <= row) ? v.y : 0.0;
             if (bj == 0) {
@@ -114,7 +112,7 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
 #pragma unroll
                 for (int cc = 7; cc >= 0; cc--)
                     if (!(a[cc][cc] > 0.0) || !(a[cc][cc] < 1.0e300) || !(ri[cc] == ri[cc])) first = cc;
-                atomicCAS(info + blockIdx.x, 0, r0 + j0 + first + 1);
+                atomicCAS(info_sys, 0, info_base + j0 + first + 1);
             }
         }
         __syncthreads();
@@ -264,6 +262,17 @@ leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall,
         Li[(int64_t)r * ld + cc] = v;
     }
     LEAF_TICK(6);
+    __syncthreads();   // shared memory is free again for the caller
+}
+
+// A, Linv: pointers to the (row-major, leading dimension ld) full matrices of batch 0;
+// the leaf works on rows/cols [r0, r0+128).  info[batch] receives first bad column + 1.
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_potrf_trtri_kernel(double* __restrict__ Aall, double* __restrict__ Linvall, int64_t ld,
+                        int64_t strideA, int64_t strideL, int r0, int* __restrict__ info) {
+    extern __shared__ __align__(16) double leaf_smem_dyn[];
+    leaf_body(Aall + (int64_t)blockIdx.x * strideA + (int64_t)r0 * ld + r0,
+              Linvall + (int64_t)blockIdx.x * strideL + (int64_t)r0 * ld + r0, ld, info + blockIdx.x, r0, leaf_smem_dyn);
 }
 
 }  // namespace exq

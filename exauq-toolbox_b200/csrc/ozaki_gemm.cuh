@@ -243,7 +243,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, EPI_WARPS);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -313,7 +313,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
         }
     } else {
+        // epilogue warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t acc_ph = 0;
         constexpr double LO_W = 1.0 / (double)(1ull << (W * (S - 4)));
@@ -323,22 +325,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const int row = I * BLK_C + quarter * 32 + lane;
             // 2^(ea - 40): row scale and the weight 256^-5 of the high diagonal group
             const double row_scale = pow2d(__ldg(a.expA + (int64_t)b * a.M + row) - 2 * W * 5 / 2);
-            const int* eb = a.expB + (int64_t)b * a.N + J * BLK_R;
-            double* crow = a.C + (int64_t)b * a.strideC + (int64_t)row * a.ldc + J * BLK_R;
+            const int* eb = a.expB + (int64_t)b * a.N + J * BLK_R + half * 32;
+            double* crow = a.C + (int64_t)b * a.strideC + (int64_t)row * a.ldc + J * BLK_R + half * 32;
             mbar_wait_guard(tmem_full, acc_ph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLK_R; c0 += 16) {
+            // phase 1: this warp's 32 columns of all S diagonals -> FP64 (exact int64 recombination); TMEM is handed
+            // back before any global memory is touched, so the next item's MMAs overlap the stores below
+            double z[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
                 int32_t d[S][16];
 #pragma unroll
-                for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + c0), d[u]);
+                for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + half * 32 + c0), d[u]);
                 tmem_ld_wait();
-                if (c0 + 16 == BLK_R) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
-                double z[16];
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     int64_t hi = 0, lo = 0;
@@ -348,21 +347,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     for (int u = 4; u < S; u++) lo = lo * (1 << W) + (int64_t)d[u][c];
                     double v = (double)hi;
                     if (S > 4) v = fma((double)lo, LO_W, v);
-                    z[c] = v * row_scale * pow2d(__ldg(eb + c0 + c));
+                    z[c0 + c] = v;
                 }
-                double2* cp = reinterpret_cast<double2*>(crow + c0);
-                if (a.cmode == C_STORE) {
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            // phase 2: scale and write the FP64 tile row
 #pragma unroll
-                    for (int c = 0; c < 8; c++) cp[c] = make_double2(z[2 * c], z[2 * c + 1]);
-                } else if (a.cmode == C_NEG) {
+            for (int c = 0; c < 32; c++) z[c] = z[c] * row_scale * pow2d(__ldg(eb + c));
+            double2* cp = reinterpret_cast<double2*>(crow);
+            if (a.cmode == C_STORE) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) cp[c] = make_double2(-z[2 * c], -z[2 * c + 1]);
-                } else {   // C_SUB
+                for (int c = 0; c < 16; c++) cp[c] = make_double2(z[2 * c], z[2 * c + 1]);
+            } else if (a.cmode == C_NEG) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        double2 o = cp[c];
-                        cp[c] = make_double2(o.x - z[2 * c], o.y - z[2 * c + 1]);
-                    }
+                for (int c = 0; c < 16; c++) cp[c] = make_double2(-z[2 * c], -z[2 * c + 1]);
+            } else {   // C_SUB
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    double2 o = cp[c];
+                    cp[c] = make_double2(o.x - z[2 * c], o.y - z[2 * c + 1]);
                 }
             }
             acc_ph ^= 1u;

@@ -23,8 +23,10 @@
 //   warp 1     single-thread tcgen05.mma issuer (cta_group::1, M = 128, K = 32, N = 64 m: one digit of the
 //              128-row operand against up to 4 consecutive digits of the 64-row operand per instruction),
 //              commits to the stage's "empty" barrier and, after the last k block, to "tmem_full"
-//   warps 2-5  epilogue: tcgen05.ld of the S diagonals, exact int64 recombination, row scaling,
-//              per-candidate sum of squares over the 64 rows of the block -> P[rowblock][cand]
+//   warps 2-9  epilogue: tcgen05.ld of the S diagonals, exact int64 recombination, row scaling,
+//              per-candidate sum of squares over 32 of the 64 rows of the block -> P[2 rowblock + half][cand].
+//              A warp may only read the TMEM lane quarter (warp % 4); two warps share a quarter and split the
+//              64 columns, which halves the time the accumulators are held before the next item's MMAs may start.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -40,7 +42,8 @@ constexpr int BLK_C = 128;      // candidates per tile  (UMMA M, TMEM lanes)
 constexpr int BLK_R = 64;       // Linv rows per tile   (UMMA N, TMEM columns per diagonal)
 constexpr int BLK_K = 64;       // k bytes per stage (one SWIZZLE_64B row)
 constexpr int UMMA_K = 32;      // k per tcgen05.mma for 8-bit operands
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter: 32 columns each)
+constexpr int EPI_WARPS = 8;
 constexpr int RASTER_G = 8;     // candidate tiles per L2 group
 
 template <int S>
@@ -191,7 +194,7 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
 
 struct Args {
     const int* row_exp;   // exponent of every Linv row
-    double* P;            // [Np / 64][ldp] per-row-block column sums of squares
+    double* P;            // [2 Np / 64][ldp] column sums of squares per half row block (32 rows of Linv)
     int64_t ldp;
     int n_ctile;          // candidate tiles (Mc / 128)
     int n_rblk;           // row blocks (Np / 64)
@@ -234,7 +237,7 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
             mbar_init(&empty[s], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, EPI_WARPS);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -304,8 +307,9 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t acc_ph = 0;
         constexpr double LO_W = 1.0 / (double)(1ull << (W * (S - 4)));   // weight of the low group relative to the high one
@@ -314,19 +318,15 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
             decode_item(i, a.n_ctile, a.n_rblk, ct, j);
             mbar_wait_guard(tmem_full, acc_ph);
             tc_fence_after();
-            double sum = 0.0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLK_R; c0 += 16) {
+            // phase 1: drain this warp's 32 columns of every diagonal into FP64 (exact int64 recombination), then hand
+            // TMEM back at once -- the scaling and the sum of squares below overlap the next item's MMAs
+            double z[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
                 int32_t d[S][16];
 #pragma unroll
-                for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + c0), d[u]);
+                for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + half * 32 + c0), d[u]);
                 tmem_ld_wait();
-                if (c0 + 16 == BLK_R) {
-                    // every accumulator value of this item is in registers: hand TMEM back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty);
-                }
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     // diagonals u = 0..3 (weights 256^-2 .. 256^-5) and u = 4..S-1, each combined exactly
@@ -335,13 +335,23 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                     for (int u = 0; u < 4 && u < S; u++) hi = hi * (1 << W) + (int64_t)d[u][c];
 #pragma unroll
                     for (int u = 4; u < S; u++) lo = lo * (1 << W) + (int64_t)d[u][c];
-                    double z = (double)hi;
-                    if (S > 4) z = fma((double)lo, LO_W, z);
-                    z *= pow2d(__ldg(a.row_exp + j * BLK_R + c0 + c));
-                    sum = fma(z, z, sum);
+                    double v = (double)hi;
+                    if (S > 4) v = fma((double)lo, LO_W, v);
+                    z[c0 + c] = v;
                 }
             }
-            a.P[(int64_t)j * a.ldp + (int64_t)ct * BLK_C + quarter * 32 + lane] = sum * a.out_scale;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+            // phase 2
+            double sum = 0.0;
+            const int* re = a.row_exp + j * BLK_R + half * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const double zz = z[c] * pow2d(__ldg(re + c));
+                sum = fma(zz, zz, sum);
+            }
+            a.P[(int64_t)(2 * j + half) * a.ldp + (int64_t)ct * BLK_C + quarter * 32 + lane] = sum * a.out_scale;
             acc_ph ^= 1u;
         }
     }
@@ -390,7 +400,7 @@ inline cudaError_t set_attrs() {
     return cudaFuncSetAttribute(colsumsq_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
 }
 
-// P[j][c] = sum over the 64 rows of block j of (Linv k_c)^2, from sliced operands.
+// P[2 j + h][c] = sum over rows 32 h .. 32 h + 31 of block j of (Linv k_c)^2, from sliced operands.
 // cand_planes: [S][Mc][Np] (global exponent cand_exp), linv_planes: [S][Np][Np] with row_exp.
 template <int S>
 inline int launch_colsumsq(const int8_t* cand_planes, int Mc, int cand_exp, const int8_t* linv_planes, const int* row_exp,

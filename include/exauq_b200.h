@@ -77,6 +77,13 @@ int exq_guard_counts(int64_t* widened, int64_t* fallbacks); /* how often each ru
  * alpha += Linv^T Linv r.  Keeps the predictive mean k^T alpha (mogp GaussianProcess.predict,
  * exauq/core/emulators.py:649) at the level of a backward-stable FP64 solve for ill-conditioned K. */
 int exq_set_refine_steps(int steps);
+/* Fused sub-tree kernel (csrc/fused_node.cuh): diagonal blocks of up to max_rows rows (256..1024, default 512;
+ * 0 = off: one launch per leaf and per node GEMM as in round 1) are factored and inverted by one launch, a
+ * thread-block cluster of cluster_ctas CTAs per system (0 = automatic: 16 for up to 8 systems, else 8).
+ * EXQ_FUSE_N / EXQ_FUSE_G.  Same arithmetic either way (FP64 DMMA): used by tests to compare the two paths. */
+int exq_set_fused(int max_rows, int cluster_ctas);
+/* current max_rows and how many clusters of 8 / 16 CTAs of that kernel the device co-schedules */
+int exq_fused_info(int* max_rows, int* clusters8, int* clusters16);
 /* kappa of the last exq_gp_fit of this handle and whether the guard sent that fit to FP64 DMMA */
 int exq_gp_kappa(exq_gp_t gp, double* kappa, int* on_fp64);
 /* int8 operations (2 per multiply-accumulate) oz::gemm_kernel issues for B systems of an M x N x K product with
@@ -97,7 +104,8 @@ int exq_timer_stop(double* ms);
 #define EXQ_PROF_STREAM 4       /* per-candidate epilogue, PEI update/argmax, vector kernels */
 #define EXQ_PROF_GEMM_FACTOR_I8 5 /* large nodes of the recursion + LAUUM on the int8 tensor cores (flops: FP64-equivalent) */
 #define EXQ_PROF_SLICE 6          /* exponent + base-256 digit passes feeding the int8 kernels (bytes moved) */
-#define EXQ_PROF_NCLASS 7
+#define EXQ_PROF_FUSED 7          /* fused sub-tree kernel: potrf + trtri of diagonal blocks <= 512 rows in one launch */
+#define EXQ_PROF_NCLASS 8
 int exq_prof_enable(int class_mask); /* bit i set: time launches of class i with event pairs */
 int exq_prof_reset(void);
 int exq_prof_get(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes);

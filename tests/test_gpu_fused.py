@@ -1,0 +1,86 @@
+"""The fused sub-tree kernel (csrc/fused_node.cuh: one cluster launch factors and inverts a diagonal block of up
+to 512 / 1024 rows) against the launch-per-step recursion it replaces and against the oracle.  Both paths run
+the same FP64 DMMA arithmetic in the same k order, so their results must agree to the last bits; the oracle
+comparison is the parity gate proper (mogp fit / logposterior behind exauq/core/emulators.py:418-450)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def exq():
+    import exauq_toolbox_b200 as m
+
+    m._lib.init(0)
+    yield m
+    m._lib.set_fused(512, 0)
+    m._lib.set_int8_digits(6, 7)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import gp_oracle
+
+    return gp_oracle
+
+
+def _run(exq, X, y, raw, thetas):
+    dev = exq.DeviceGP(X, y, "Matern52").fit(raw, 1.7, 0.0)
+    out = {"nll": dev.neg_log_likelihood, "loo": dev.loo()}
+    out["val"], out["grad"], out["info"], _ = dev.logpost_batch(thetas, 0.0)
+    dev.close()
+    return out
+
+
+def test_device_offers_clusters(exq):
+    info = exq._lib.fused_info()
+    assert info["max_rows"] == 512 and info["clusters_of_8"] >= 1
+
+
+@pytest.mark.parametrize("N,d", [(200, 3), (500, 4), (600, 2), (1500, 5), (1025, 6), (4096, 8)])
+def test_fused_equals_launch_per_step(exq, orc, N, d):
+    """Shapes: one fused launch for everything (Np <= 512), odd splits (Np = 640: 384 + 256; 1536: 768 -> 384 + 384),
+    a 1-row overhang (Np = 1152 = 9 blocks) and the benchmark size, with 1, 5 and 15 systems per launch."""
+    lib = exq._lib
+    X, y = orc.synthetic_problem(N, d)
+    raw = np.full(d, -2 * np.log(0.5))
+    rng = np.random.default_rng(N)
+    R = 15 if N <= 1500 else 5
+    thetas = np.concatenate([raw + rng.uniform(-0.6, 0.6, (R, d)), np.log(1.7) + rng.uniform(-0.4, 0.4, (R, 1))], axis=1)
+    lib.set_fused(0, 0)
+    ref = _run(exq, X, y, raw, thetas)
+    for rows, G in [(512, 0), (512, 8), (256, 4), (1024, 8), (512, 1)]:
+        lib.set_fused(rows, G)
+        got = _run(exq, X, y, raw, thetas)
+        assert np.all(got["info"] == 0)
+        assert abs(got["nll"] - ref["nll"]) <= 1e-14 * abs(ref["nll"]), (rows, G)
+        for a, b in zip(got["loo"], ref["loo"]):
+            assert np.allclose(a, b, rtol=1e-12, atol=1e-14), (rows, G)
+        assert np.allclose(got["val"], ref["val"], rtol=1e-14, atol=0), (rows, G)
+        assert np.allclose(got["grad"], ref["grad"], rtol=1e-10, atol=1e-12 * np.max(np.abs(ref["grad"]))), (rows, G)
+    lib.set_fused(512, 0)
+
+
+def test_fused_against_oracle(exq, orc):
+    lib = exq._lib
+    lib.set_fused(512, 0)
+    N, d = 900, 4
+    X, y = orc.synthetic_problem(N, d)
+    raw = np.full(d, -2 * np.log(0.4))
+    dev = exq.DeviceGP(X, y, "Matern52").fit(raw, 1.7, 1e-8)
+    ref = orc.fit(X, y, "Matern52", raw, 1.7, 1e-8)
+    onll = orc.neg_log_likelihood(ref)
+    assert abs(dev.neg_log_likelihood - onll) <= 1e-9 * abs(onll)
+    Xc = orc.synthetic_candidates(1000, d)
+    m, v = dev.predict(Xc)
+    mo, vo = orc.predict(ref, Xc)
+    assert np.all(np.abs(m - mo) <= np.maximum(1e-8 * np.abs(mo), 1e-9))
+    assert np.all(np.abs(v - vo) <= np.maximum(1e-8 * np.abs(vo), 1e-9))
+    th = np.concatenate([raw, [np.log(1.7)]])
+    val, grad, info, _ = dev.logpost_batch(th[None, :], 1e-8)
+    oval, ograd = orc.neg_log_likelihood_grad(X, y, "Matern52", th, 1e-8)
+    assert info[0] == 0 and abs(val[0] - oval) <= 1e-9 * abs(oval)
+    assert np.all(np.abs(grad[0] - ograd) <= 1e-7 * np.max(np.abs(ograd)))
+    dev.close()
