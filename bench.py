@@ -332,7 +332,7 @@ def run_b200(a):
            | (1 << _lib.PROF_ASSEMBLE))
     if not _lib.factor_slices():
         big |= 1 << _lib.PROF_GEMM_FACTOR
-    names = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_factor_i8", "slice"]
+    names = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_factor_i8", "slice", "fused"]
     _lib.prof_enable(big)
     _lib.prof_reset()
     sampler = ClockSampler(local)
@@ -504,7 +504,14 @@ def run_b200(a):
                          "runs on tcgen05 kind::i8 with exact int32 accumulation in TMEM when variance_slices > 0",
                     variance_slices=slices)
     other = {k: v for k, v in kern.items() if k != dominant}
-    for name in ("leaf", "assemble", "slice"):
+    pf = prof["fused"]
+    if pf["launches"]:
+        other["fused_factor_kernel[potrf+trtri of 512-row diagonal blocks, one cluster launch each]"] = {
+            "ms_per_step": pf["ms"] / a.steps, "launches_per_step": pf["launches"] / a.steps,
+            "avg_launch_ms": pf["ms"] / pf["launches"], "bound": "latency (leaf pivot chain) / FP64 DMMA",
+            "achieved": pf["flops"] / (pf["ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": pf["flops"] / (pf["ms"] * 1e-3) / 1e12 / fp64_peak}
+    for name in ("leaf", "assemble", "slice", "stream"):
         p = prof[name]
         if p["launches"]:
             other[name] = {"ms_per_step": p["ms"] / a.steps, "launches_per_step": p["launches"] / a.steps,

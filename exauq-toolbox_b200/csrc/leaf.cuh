@@ -57,12 +57,26 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         while (rem >= LEAF_NBLK - bj) { rem -= LEAF_NBLK - bj; bj++; }
         int bi = bj + rem;
         tb[s] = (q < 136) ? ((bi << 8) | bj) : -1;
+    }
+    // all 17 tile loads of a thread are issued before the first one is consumed (the index search above used to sit
+    // between them and serialised 17 L2 round trips: 12 k of the leaf's 80 k cycles)
+    double2 tile_in[LEAF_SLOTS];
+#pragma unroll
+    for (int s = 0; s < LEAF_SLOTS; s++) {
+        tile_in[s] = make_double2(0.0, 0.0);
+        if (tb[s] >= 0) {
+            const int row = 8 * (tb[s] >> 8) + g, col = 8 * (tb[s] & 255) + 2 * t;
+            tile_in[s] = __ldcg(reinterpret_cast<const double2*>(A + (int64_t)row * ld + col));
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < LEAF_SLOTS; s++) {
         c[s][0] = c[s][1] = 0.0;
         if (tb[s] >= 0) {
-            int row = 8 * bi + g, col = 8 * bj + 2 * t;
-            double2 v = __ldcg(reinterpret_cast<const double2*>(A + (int64_t)row * ld + col));
-            c[s][0] = (col <= row) ? v.x : 0.0;
-            c[s][1] = (col + 1 <= row) ? v.y : 0.0;
+            const int bi = tb[s] >> 8, bj = tb[s] & 255;
+            const int row = 8 * bi + g, col = 8 * bj + 2 * t;
+            c[s][0] = (col <= row) ? tile_in[s].x : 0.0;
+            c[s][1] = (col + 1 <= row) ? tile_in[s].y : 0.0;
             if (bj == 0) {
                 S[row * LEAF_LD + col] = c[s][0];
                 S[row * LEAF_LD + col + 1] = c[s][1];
@@ -73,50 +87,55 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
     LEAF_TICK(0);
 
     // ================= phase 1: Cholesky =================================================
-    for (int p = 0; p < LEAF_NBLK; p++) {
-        const int j0 = 8 * p;
-        // (a) 8 x 8 diagonal block, warp 0.  Every lane factors the whole block redundantly in
-        // registers (36 broadcast loads, no shuffles on the 8-pivot dependency chain).
-        if (warp == 0) {
-            double a[8][8];
+    // 8 x 8 diagonal block at j0, warp 0.  Every lane factors the whole block redundantly in
+    // registers (36 broadcast loads, no shuffles on the 8-pivot dependency chain).
+    auto diag_factor = [&](int j0) {
+        double a[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int cc = 0; cc <= r; cc++) a[r][cc] = S[(j0 + r) * LEAF_LD + j0 + cc];
+        double ri[8];
+        bool bad = false;
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) {
+            const double d = a[cc][cc];
+            bad = bad || !(d > 0.0) || !(d < 1.0e300);
+            ri[cc] = rsqrt(d);
+            a[cc][cc] = d * ri[cc];
+#pragma unroll
+            for (int r = cc + 1; r < 8; r++) a[r][cc] *= ri[cc];
+#pragma unroll
+            for (int c2 = cc + 1; c2 < 8; c2++)
+#pragma unroll
+                for (int r = c2; r < 8; r++) a[r][c2] -= a[r][cc] * a[c2][cc];
+        }
+        if (lane < 8) {
 #pragma unroll
             for (int r = 0; r < 8; r++)
+                if (r == lane) {
 #pragma unroll
-                for (int cc = 0; cc <= r; cc++) a[r][cc] = S[(j0 + r) * LEAF_LD + j0 + cc];
-            double ri[8];
-            bool bad = false;
-#pragma unroll
-            for (int cc = 0; cc < 8; cc++) {
-                const double d = a[cc][cc];
-                bad = bad || !(d > 0.0) || !(d < 1.0e300);
-                ri[cc] = rsqrt(d);
-                a[cc][cc] = d * ri[cc];
-#pragma unroll
-                for (int r = cc + 1; r < 8; r++) a[r][cc] *= ri[cc];
-#pragma unroll
-                for (int c2 = cc + 1; c2 < 8; c2++)
-#pragma unroll
-                    for (int r = c2; r < 8; r++) a[r][c2] -= a[r][cc] * a[c2][cc];
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int r = 0; r < 8; r++)
-                    if (r == lane) {
-#pragma unroll
-                        for (int cc = 0; cc <= r; cc++) S[(j0 + r) * LEAF_LD + j0 + cc] = a[r][cc];
-                        rinv[j0 + r] = ri[r];
-                    }
-            }
-            if (lane == 0 && bad) {
-                int first = 0;
-#pragma unroll
-                for (int cc = 7; cc >= 0; cc--)
-                    if (!(a[cc][cc] > 0.0) || !(a[cc][cc] < 1.0e300) || !(ri[cc] == ri[cc])) first = cc;
-                atomicCAS(info_sys, 0, info_base + j0 + first + 1);
-            }
+                    for (int cc = 0; cc <= r; cc++) S[(j0 + r) * LEAF_LD + j0 + cc] = a[r][cc];
+                    rinv[j0 + r] = ri[r];
+                }
         }
-        __syncthreads();
-        LEAF_TICK(1);
+        if (lane == 0 && bad) {
+            int first = 0;
+#pragma unroll
+            for (int cc = 7; cc >= 0; cc--)
+                if (!(a[cc][cc] > 0.0) || !(a[cc][cc] < 1.0e300) || !(ri[cc] == ri[cc])) first = cc;
+            atomicCAS(info_sys, 0, info_base + j0 + first + 1);
+        }
+    };
+    // Step p: (b) panel below diagonal block p, (c1) rank-8 update of block column p + 1 only, then -- one step of
+    // look-ahead -- warp 0 factors diagonal block p + 1 WHILE the other warps (and warp 0 afterwards) apply the
+    // rank-8 update to the rest of the trailing matrix (c2).  The 8-pivot chain (1400 cycles) used to be a phase of
+    // its own with 7 warps idle: 22 k of the leaf's 80 k cycles.
+    if (warp == 0) diag_factor(0);
+    __syncthreads();
+    LEAF_TICK(1);
+    for (int p = 0; p < LEAF_NBLK; p++) {
+        const int j0 = 8 * p;
         // (b) rows below the diagonal block: forward substitution with L11; warp 7 inverts L11
         {
             const int r = j0 + 8 + tid;
@@ -155,13 +174,11 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         // (c) rank-8 update of every trailing tile, in registers.  Tiles are enumerated column-major,
         // so the tiles with bj > p are a contiguous SUFFIX of this warp's slots: enter the unrolled
         // slot sequence at the first active one (no per-slot branch, loads and DMMAs of successive
-        // slots overlap).
-        {
-            const int q0 = 16 * (p + 1) - ((p + 1) * p) / 2;          // first tile of block column p+1
-            const int q1 = 16 * (p + 2) - ((p + 2) * (p + 1)) / 2;    // first tile of block column p+2
-            const int smin = (q0 - warp + 7) >> 3;
-#define LEAF_SLOT_UPDATE(SL)                                                              \
-    if (tb[SL] >= 0) {                                                                    \
+        // slots overlap).  Block column p + 1 (tiles q0 <= q < q1) goes first and is published to S.
+        const int q0 = 16 * (p + 1) - ((p + 1) * p) / 2;          // first tile of block column p+1
+        const int q1 = 16 * (p + 2) - ((p + 2) * (p + 1)) / 2;    // first tile of block column p+2
+#define LEAF_SLOT_UPDATE(SL, FIRST_COLUMN)                                                \
+    if (tb[SL] >= 0 && ((warp + 8 * SL < q1) == (FIRST_COLUMN))) {                        \
         const int bi = tb[SL] >> 8, bj = tb[SL] & 255;                                    \
         double a0 = S[(8 * bi + g) * LEAF_LD + j0 + t];                                   \
         double a1 = S[(8 * bi + g) * LEAF_LD + j0 + 4 + t];                               \
@@ -169,34 +186,43 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         double b1 = S[(8 * bj + g) * LEAF_LD + j0 + 4 + t];                               \
         dmma884(c[SL][0], c[SL][1], -a0, b0);                                             \
         dmma884(c[SL][0], c[SL][1], -a1, b1);                                             \
-        if (warp + 8 * SL < q1) {                                                         \
+        if (FIRST_COLUMN) {                                                               \
             int row = 8 * bi + g, col = 8 * bj + 2 * t;                                   \
             S[row * LEAF_LD + col] = c[SL][0];                                            \
             S[row * LEAF_LD + col + 1] = c[SL][1];                                        \
         }                                                                                 \
     }
-            switch (smin < 0 ? 0 : smin) {
-                case 0: LEAF_SLOT_UPDATE(0)
-                case 1: LEAF_SLOT_UPDATE(1)
-                case 2: LEAF_SLOT_UPDATE(2)
-                case 3: LEAF_SLOT_UPDATE(3)
-                case 4: LEAF_SLOT_UPDATE(4)
-                case 5: LEAF_SLOT_UPDATE(5)
-                case 6: LEAF_SLOT_UPDATE(6)
-                case 7: LEAF_SLOT_UPDATE(7)
-                case 8: LEAF_SLOT_UPDATE(8)
-                case 9: LEAF_SLOT_UPDATE(9)
-                case 10: LEAF_SLOT_UPDATE(10)
-                case 11: LEAF_SLOT_UPDATE(11)
-                case 12: LEAF_SLOT_UPDATE(12)
-                case 13: LEAF_SLOT_UPDATE(13)
-                case 14: LEAF_SLOT_UPDATE(14)
-                case 15: LEAF_SLOT_UPDATE(15)
-                case 16: LEAF_SLOT_UPDATE(16)
-                default: break;
-            }
+#define LEAF_ALL_SLOTS(FROM, FIRST_COLUMN)                                                \
+    switch (FROM) {                                                                       \
+        case 0: LEAF_SLOT_UPDATE(0, FIRST_COLUMN)                                         \
+        case 1: LEAF_SLOT_UPDATE(1, FIRST_COLUMN)                                         \
+        case 2: LEAF_SLOT_UPDATE(2, FIRST_COLUMN)                                         \
+        case 3: LEAF_SLOT_UPDATE(3, FIRST_COLUMN)                                         \
+        case 4: LEAF_SLOT_UPDATE(4, FIRST_COLUMN)                                         \
+        case 5: LEAF_SLOT_UPDATE(5, FIRST_COLUMN)                                         \
+        case 6: LEAF_SLOT_UPDATE(6, FIRST_COLUMN)                                         \
+        case 7: LEAF_SLOT_UPDATE(7, FIRST_COLUMN)                                         \
+        case 8: LEAF_SLOT_UPDATE(8, FIRST_COLUMN)                                         \
+        case 9: LEAF_SLOT_UPDATE(9, FIRST_COLUMN)                                         \
+        case 10: LEAF_SLOT_UPDATE(10, FIRST_COLUMN)                                       \
+        case 11: LEAF_SLOT_UPDATE(11, FIRST_COLUMN)                                       \
+        case 12: LEAF_SLOT_UPDATE(12, FIRST_COLUMN)                                       \
+        case 13: LEAF_SLOT_UPDATE(13, FIRST_COLUMN)                                       \
+        case 14: LEAF_SLOT_UPDATE(14, FIRST_COLUMN)                                       \
+        case 15: LEAF_SLOT_UPDATE(15, FIRST_COLUMN)                                       \
+        case 16: LEAF_SLOT_UPDATE(16, FIRST_COLUMN)                                       \
+        default: break;                                                                   \
+    }
+        const int smin = (q0 - warp + 7) >> 3;                    // first slot with q >= q0
+        const int smin2 = (q1 - warp + 7) >> 3;                   // first slot with q >= q1
+        // (c1) block column p + 1: at most two slots per warp; later slots fail the (q < q1) test at once
+        LEAF_ALL_SLOTS(smin < 0 ? 0 : smin, true)
+        __syncthreads();
+        // (a, one step ahead) + (c2)
+        if (warp == 0 && p + 1 < LEAF_NBLK) diag_factor(j0 + 8);
+        LEAF_ALL_SLOTS(smin2 < 0 ? 0 : smin2, false)
+#undef LEAF_ALL_SLOTS
 #undef LEAF_SLOT_UPDATE
-        }
         __syncthreads();
         LEAF_TICK(3);
     }
@@ -251,15 +277,24 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
     LEAF_TICK(5);
     __syncthreads();
 
-    // ---- write back L (upper zeroed) and Linv (full tile, zeros above the diagonal) ----
-    for (int idx = tid; idx < LEAF_N * LEAF_N; idx += LEAF_THREADS) {
-        int r = idx >> 7, cc = idx & 127;
-        A[(int64_t)r * ld + cc] = (cc <= r) ? S[r * LEAF_LD + cc] : 0.0;
-        int br = r >> 3, bc = cc >> 3;
-        double v = 0.0;
-        if (bc < br) v = S[cc * LEAF_LD + r];
-        else if (bc == br) v = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7)];
-        Li[(int64_t)r * ld + cc] = v;
+    // ---- write back L (upper zeroed) and Linv (full tile, zeros above the diagonal), 16 bytes per store ----
+    for (int idx = tid; idx < LEAF_N * (LEAF_N / 2); idx += LEAF_THREADS) {
+        const int r = idx >> 6, cc = (idx & 63) << 1;
+        double2 l, x;
+        l.x = (cc <= r) ? S[r * LEAF_LD + cc] : 0.0;
+        l.y = (cc + 1 <= r) ? S[r * LEAF_LD + cc + 1] : 0.0;
+        *reinterpret_cast<double2*>(A + (int64_t)r * ld + cc) = l;
+        const int br = r >> 3, bc = cc >> 3;          // cc and cc + 1 lie in the same 8-column block
+        if (bc < br) {
+            x.x = S[cc * LEAF_LD + r];
+            x.y = S[(cc + 1) * LEAF_LD + r];
+        } else if (bc == br) {
+            x.x = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7)];
+            x.y = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7) + 1];
+        } else {
+            x.x = x.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(Li + (int64_t)r * ld + cc) = x;
     }
     LEAF_TICK(6);
     __syncthreads();   // shared memory is free again for the caller
