@@ -429,6 +429,7 @@ struct OzOperand {
     const double* p;   // sub-matrix origin inside a system (leading dimension Np, system stride Np^2)
     int trans;         // 0: p[row][k], 1: p[k][row]
     int mask;          // oz::MASK_*: which side of the operand's diagonal holds data
+    const double* sumsq = nullptr;   // transposed operands: sum_k p[k][row]^2 per system (stride Np) if already known
 };
 
 // digit planes of both operands (A in the first half of the per-system workspace, B in the second; one operand
@@ -462,7 +463,7 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     int8_t* planesB = same ? planesA : s.oz_planes + (s.oz_per_sys / 2) * s.B;
     // reuse_a: the digit planes of A are still in place from the previous product of this node
     ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)s.B * K * ((reuse_a ? 0 : M) + (same ? 0 : N)) * (16.0 + S));
-    if (!reuse_a) oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream);
+    if (!reuse_a) oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream, A.sumsq, s.Np);
     if (!same) oz::slice_operand<S>(Bm.p, ld, sq, N, K, s.B, Bm.trans, Bm.mask, expB, planesB, g.stream);
     prof_end(m);
     g.launches += (reuse_a ? 0 : (A.trans ? 2 : 1)) + (same ? 0 : (Bm.trans ? 2 : 1)) - 1;
@@ -647,15 +648,17 @@ int refine_alpha(Sys& s, const double* X, int64_t strideX, const double* y, int6
     return EXQ_OK;
 }
 
-// K^-1 (lower tiles) into s.W; digits: base-256 digits of the int8 product (0: the configured LAUUM digits)
-int lauum(Sys& s, int digits = 0) {
+// K^-1 (lower tiles) into s.W; digits: base-256 digits of the int8 product (0: the configured LAUUM digits);
+// have_dinv: s.dinv holds the column sums of squares of Linv (solve_vectors ran on these systems)
+int lauum(Sys& s, int digits = 0, bool have_dinv = false) {
     GemmArgs a{};
     a.lda = a.ldb = a.ldc = s.Np;
     a.strideA = a.strideB = a.strideC = s.sq();
     a.A = s.Linv; a.B = s.Linv; a.C = s.W; a.M = a.N = a.K = s.Np;
     a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
     if (oz_gemm_wanted(s, s.Np, s.Np, s.Np, true))
-        return oz_gemm(s, {s.Linv, 1, oz::MASK_GE}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np, s.Np, KR_GE_I, 1, C_STORE,
+        return oz_gemm(s, {s.Linv, 1, oz::MASK_GE, have_dinv ? s.dinv : nullptr}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np,
+                       s.Np, KR_GE_I, 1, C_STORE,
                        false, digits ? std::min(digits, g.oz_factor_slices) : std::min(g.oz_lauum_slices, g.oz_factor_slices));
     return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
 }
@@ -887,7 +890,7 @@ int enqueue_factor(exq_gp_t gp, Sys& s, const double* theta_host) {
 int enqueue_grad(exq_gp_t gp, Sys& s, int dmax, int lauum_digits) {
     const int N = (int)gp->N, d = gp->d, Np = gp->Np, nt = Np / 128, B = s.B;
     int rc;
-    if ((rc = lauum(s, lauum_digits))) return rc;
+    if ((rc = lauum(s, lauum_digits, /*have_dinv=*/true))) return rc;
     size_t smem = ((size_t)128 * d + (size_t)d * GRAD_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
     dim3 grid(nt, nt, B);
     ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)B * N * N * 0.5 * (5.0 * d + 40.0), (double)B * N * N * 4.0);

@@ -9,8 +9,9 @@
 //
 // Layout: S[128][132] holds L in the lower triangle; the strictly-upper part is reused to
 // hold Linv TRANSPOSED (Linv[r][c], r > c, lives at S[c][r]); the sixteen 8 x 8 diagonal
-// blocks of Linv live in XD.  The 136 lower 8 x 8 tiles are owned round-robin by the 8
-// warps and stay in DMMA accumulator registers between steps (left-looking at tile level).
+// blocks of Linv live in XD.  The 136 lower 8 x 8 tiles are owned round-robin by warps 1..7
+// and stay in DMMA accumulator registers between steps; warp 0 runs the 8-pivot chain of the
+// next diagonal block while they apply the rank-8 update of the current one.
 #pragma once
 #include "exq_common.cuh"
 
@@ -24,7 +25,8 @@ __device__ long long leaf_prof[64];
 #endif
 
 constexpr int LEAF_N = 128, LEAF_LD = 132, LEAF_NBLK = 16, LEAF_THREADS = 256;
-constexpr int LEAF_SLOTS = 17;        // 136 tiles / 8 warps
+constexpr int LEAF_OWNERS = 7;        // warps 1..7 own the 136 tiles; warp 0 keeps the pivot chain one step ahead
+constexpr int LEAF_SLOTS = 20;        // ceil(136 / 7)
 constexpr int LEAF_XD_LD = 12;
 constexpr int LEAF_SMEM_DOUBLES =
     LEAF_N * LEAF_LD + LEAF_NBLK * 8 * LEAF_XD_LD + LEAF_N + 8 * 8 * LEAF_XD_LD;
@@ -52,11 +54,11 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
     double c[LEAF_SLOTS][2];
 #pragma unroll
     for (int s = 0; s < LEAF_SLOTS; s++) {
-        int q = warp + 8 * s;
+        int q = (warp - 1) + LEAF_OWNERS * s;
         int bj = 0, rem = q;
-        while (rem >= LEAF_NBLK - bj) { rem -= LEAF_NBLK - bj; bj++; }
+        while (rem >= LEAF_NBLK - bj && bj < LEAF_NBLK) { rem -= LEAF_NBLK - bj; bj++; }
         int bi = bj + rem;
-        tb[s] = (q < 136) ? ((bi << 8) | bj) : -1;
+        tb[s] = (warp > 0 && q < 136) ? ((bi << 8) | bj) : -1;
     }
     // all 17 tile loads of a thread are issued before the first one is consumed (the index search above used to sit
     // between them and serialised 17 L2 round trips: 12 k of the leaf's 80 k cycles)
@@ -178,7 +180,7 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         const int q0 = 16 * (p + 1) - ((p + 1) * p) / 2;          // first tile of block column p+1
         const int q1 = 16 * (p + 2) - ((p + 2) * (p + 1)) / 2;    // first tile of block column p+2
 #define LEAF_SLOT_UPDATE(SL, FIRST_COLUMN)                                                \
-    if (tb[SL] >= 0 && ((warp + 8 * SL < q1) == (FIRST_COLUMN))) {                        \
+    if (tb[SL] >= 0 && (((warp - 1) + LEAF_OWNERS * SL < q1) == (FIRST_COLUMN))) {       \
         const int bi = tb[SL] >> 8, bj = tb[SL] & 255;                                    \
         double a0 = S[(8 * bi + g) * LEAF_LD + j0 + t];                                   \
         double a1 = S[(8 * bi + g) * LEAF_LD + j0 + 4 + t];                               \
@@ -211,16 +213,23 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         case 14: LEAF_SLOT_UPDATE(14, FIRST_COLUMN)                                       \
         case 15: LEAF_SLOT_UPDATE(15, FIRST_COLUMN)                                       \
         case 16: LEAF_SLOT_UPDATE(16, FIRST_COLUMN)                                       \
+        case 17: LEAF_SLOT_UPDATE(17, FIRST_COLUMN)                                       \
+        case 18: LEAF_SLOT_UPDATE(18, FIRST_COLUMN)                                       \
+        case 19: LEAF_SLOT_UPDATE(19, FIRST_COLUMN)                                       \
         default: break;                                                                   \
     }
-        const int smin = (q0 - warp + 7) >> 3;                    // first slot with q >= q0
-        const int smin2 = (q1 - warp + 7) >> 3;                   // first slot with q >= q1
-        // (c1) block column p + 1: at most two slots per warp; later slots fail the (q < q1) test at once
-        LEAF_ALL_SLOTS(smin < 0 ? 0 : smin, true)
+        // first slot of this warp with q >= q0 / q >= q1 (q = warp - 1 + 7 s)
+        const int smin = (q0 - (warp - 1) + LEAF_OWNERS - 1) / LEAF_OWNERS;
+        const int smin2 = (q1 - (warp - 1) + LEAF_OWNERS - 1) / LEAF_OWNERS;
+        // (c1) block column p + 1: at most three slots per warp; later slots fail the (q < q1) test at once
+        if (warp > 0) { LEAF_ALL_SLOTS(smin < 0 ? 0 : smin, true) }
         __syncthreads();
-        // (a, one step ahead) + (c2)
-        if (warp == 0 && p + 1 < LEAF_NBLK) diag_factor(j0 + 8);
-        LEAF_ALL_SLOTS(smin2 < 0 ? 0 : smin2, false)
+        // (a, one step ahead) by warp 0, which owns no tiles, beside (c2) by warps 1..7
+        if (warp == 0) {
+            if (p + 1 < LEAF_NBLK) diag_factor(j0 + 8);
+        } else {
+            LEAF_ALL_SLOTS(smin2 < 0 ? 0 : smin2, false)
+        }
 #undef LEAF_ALL_SLOTS
 #undef LEAF_SLOT_UPDATE
         __syncthreads();

@@ -58,6 +58,18 @@ __global__ void __launch_bounds__(256) operand_exponent_kernel(const double* __r
     }
 }
 
+// exponents of the COLUMNS of an inverse factor from its column sums of squares (dinv_j = sum_k Linv[k][j]^2, which
+// the triangular mat-vec pass has already produced): max_k |Linv[k][j]| <= sqrt(dinv_j), and >= sqrt(dinv_j / n), so
+// the exponent is at most log2(sqrt n) = 6 bits (n = 4096) looser than the exact one -- usually 1-2, the diagonal entry
+// carries most of a column's mass.  Saves the separate exponent pass over the whole matrix in front of LAUUM.
+__global__ void __launch_bounds__(256) exponent_from_sumsq_kernel(const double* __restrict__ sumsq, int64_t stride, int n,
+                                                                  int* __restrict__ row_exp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double bound = sqrt(sumsq[(int64_t)blockIdx.z * stride + j]) * 1.0000001;
+    row_exp[(int64_t)blockIdx.z * n + j] = scale_exponent(bound);
+}
+
 // digits of S planes from a double scaled by 2^(8S - e)
 template <int S>
 __device__ __forceinline__ unsigned long long digits_of(double v, double sc) {
@@ -388,10 +400,18 @@ inline cudaError_t set_gemm_attrs() {
 }
 
 // One operand of an int8 GEMM: exponents + digit planes for a batch of B matrices (rows x K each)
+// sumsq != nullptr (transposed operands only): row exponents from the column sums of squares instead of a pass over src
 template <int S>
 inline void slice_operand(const double* src, int64_t ld, int64_t stride_sys, int rows, int K, int B, int trans, int mask,
-                          int* row_exp, int8_t* planes, cudaStream_t stream) {
+                          int* row_exp, int8_t* planes, cudaStream_t stream, const double* sumsq = nullptr,
+                          int64_t sumsq_stride = 0) {
     const int64_t plane_bytes = (int64_t)B * rows * K;
+    if (trans && sumsq) {
+        exponent_from_sumsq_kernel<<<dim3((rows + 255) / 256, 1, B), 256, 0, stream>>>(sumsq, sumsq_stride, rows, row_exp);
+        slice_cols_kernel<S><<<dim3(rows / 64, K / 64, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
+                                                                             plane_bytes);
+        return;
+    }
     if (!trans) {
         slice_rows_kernel<S><<<dim3((rows + 7) / 8, 1, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
                                                                             plane_bytes);
