@@ -198,6 +198,10 @@ int set_kernel_attrs() {
     CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(assemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_fast_kernel<EXQ_KERNEL_MATERN52, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_fast_kernel<EXQ_KERNEL_MATERN52, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_fast_kernel<EXQ_KERNEL_SQEXP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_TRY(cudaFuncSetAttribute(grad_fast_kernel<EXQ_KERNEL_SQEXP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CUDA_TRY(cudaFuncSetAttribute(grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -894,14 +898,25 @@ int enqueue_grad(exq_gp_t gp, Sys& s, int dmax, int lauum_digits) {
     size_t smem = ((size_t)128 * d + (size_t)d * GRAD_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
     dim3 grid(nt, nt, B);
     ProfMark m = prof_begin(EXQ_PROF_STREAM, (double)B * N * N * 0.5 * (5.0 * d + 40.0), (double)B * N * N * 4.0);
-    if (dmax == 8)
-        grad_kernel<8><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d, gp->kernel_id, s.gpartial, nt);
+#define EXQ_GRAD_ARGS gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d
+    const bool fast = g.fast_corr && gp->kernel_id != EXQ_KERNEL_PRODMAT52 && dmax <= 16;
+    if (fast && gp->kernel_id == EXQ_KERNEL_MATERN52 && dmax == 8)
+        grad_fast_kernel<EXQ_KERNEL_MATERN52, 8><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, s.gpartial, nt);
+    else if (fast && gp->kernel_id == EXQ_KERNEL_MATERN52)
+        grad_fast_kernel<EXQ_KERNEL_MATERN52, 16><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, s.gpartial, nt);
+    else if (fast && dmax == 8)
+        grad_fast_kernel<EXQ_KERNEL_SQEXP, 8><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, s.gpartial, nt);
+    else if (fast)
+        grad_fast_kernel<EXQ_KERNEL_SQEXP, 16><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, s.gpartial, nt);
+    else if (dmax == 8)
+        grad_kernel<8><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, gp->kernel_id, s.gpartial, nt);
     else if (dmax == 16)
-        grad_kernel<16><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d, gp->kernel_id, s.gpartial, nt);
+        grad_kernel<16><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, gp->kernel_id, s.gpartial, nt);
     else if (dmax == 32)
-        grad_kernel<32><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d, gp->kernel_id, s.gpartial, nt);
+        grad_kernel<32><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, gp->kernel_id, s.gpartial, nt);
     else
-        grad_kernel<64><<<grid, 256, smem, g.stream>>>(gp->X, 0, s.theta, d + 2, s.W, Np, s.sq(), s.alpha, Np, N, d, gp->kernel_id, s.gpartial, nt);
+        grad_kernel<64><<<grid, 256, smem, g.stream>>>(EXQ_GRAD_ARGS, gp->kernel_id, s.gpartial, nt);
+#undef EXQ_GRAD_ARGS
     prof_end(m);
     LAUNCH_CHECK("grad_kernel");
     m = prof_begin(EXQ_PROF_STREAM, 0.0, 0.0);
