@@ -39,6 +39,7 @@ SIGNATURES = {
     "exq_set_refine_steps": (C.c_int, [C.c_int]),
     "exq_set_fused": (C.c_int, [C.c_int, C.c_int]),
     "exq_fused_info": (C.c_int, [_ip, _ip, _ip]),
+    "exq_set_pei_fused": (C.c_int, [C.c_int]),
     "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
     "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "exq_timer_start": (C.c_int, []),
@@ -362,6 +363,12 @@ def set_fused(max_rows: int = 512, cluster_ctas: int = 0) -> None:
     """Fused sub-tree kernel: largest diagonal block handled by one launch (0 = off) and CTAs per cluster (0 = automatic)."""
     init()
     check(load().exq_set_fused(int(max_rows), int(cluster_ctas)), "exq_set_fused")
+
+
+def set_pei_fused(on: bool = True) -> None:
+    """Fused prediction / PEI pipeline (no FP64 covariance chunk) on or off (round-1 three-pass pipeline)."""
+    init()
+    check(load().exq_set_pei_fused(1 if on else 0), "exq_set_pei_fused")
 
 
 def fused_info() -> dict:

@@ -21,6 +21,7 @@
 #include "fused_node.cuh"
 #include "ozaki_i8.cuh"
 #include "ozaki_gemm.cuh"
+#include "pei_fused.cuh"
 
 using namespace exq;
 
@@ -54,6 +55,9 @@ struct Ctx {
     // KcT[chunk][Np] and the partial column sums P[Np/128][chunk]
     double *KcT = nullptr, *P = nullptr;
     size_t kct_elems = 0, p_elems = 0;
+    double* PMR = nullptr;           // [2][Np/64][chunk] partial means / repulsion products of the fused PEI pipeline
+    size_t pmr_elems = 0;
+    int pei_fused = 1;               // EXQ_PEI_FUSED=0: round-1 pipeline (FP64 chunk -> slicer -> per-candidate epilogue)
     // int8 tcgen05 variance path (ozaki_i8.cuh): digits per operand (EXQ_OZAKI_SLICES = 0 keeps the FP64 DMMA
     // GEMM, 5..7 selects the number of base-256 digits; 6 = 48 bits is ~2e-12 absolute on the variance)
     int oz_slices = 6;
@@ -675,8 +679,9 @@ int assemble_sym(Sys& s, const double* X, int64_t strideX, int nvalid, int kerne
     return launch_assemble(a, s.Np, s.Np, s.B);
 }
 
-int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk) {
-    const size_t need_k = (size_t)want_chunk * gp->Np, need_p = (size_t)(gp->Np / 32) * want_chunk;   // int8: 2 partials per 64 rows
+// kct_rows: rows of the FP64 covariance chunk actually needed (the fused PEI pipeline only keeps 128 for its <= 8-point tail)
+int ensure_pred_scratch(exq_gp_t gp, int64_t want_chunk, int64_t kct_rows = -1) {
+    const size_t need_k = (size_t)(kct_rows < 0 ? want_chunk : std::min(want_chunk, kct_rows)) * gp->Np, need_p = (size_t)(gp->Np / 32) * want_chunk;   // int8: 2 partials per 64 rows
     if (g.kct_elems < need_k) {
         cudaFree(g.KcT);
         g.KcT = nullptr; g.kct_elems = 0;
@@ -716,8 +721,19 @@ void planes_park(int8_t* p, size_t bytes) {
 }
 
 // ---- variance product on the int8 tensor cores (ozaki_i8.cuh) ---------------------------------
+int ensure_cand_planes(size_t need) {
+    if (g.cand_planes_bytes < need) {
+        cudaFree(g.cand_planes);
+        g.cand_planes = nullptr; g.cand_planes_bytes = 0;
+        CUDA_TRY(cudaMalloc(&g.cand_planes, need));
+        g.cand_planes_bytes = need;
+    }
+    return EXQ_OK;
+}
+
+// sliced = true: the digit planes of this chunk are already in g.cand_planes (assemble_digits_kernel)
 template <int S>
-int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
+int variance_ozaki_s(exq_gp_t gp, int mc_pad, bool sliced = false) {
     const int Np = gp->Np;
     if (gp->planes_S != S) {
         // digits of Linv: once per fit
@@ -745,19 +761,17 @@ int variance_ozaki_s(exq_gp_t gp, int mc_pad) {
         g.launches++;
         gp->planes_S = S;
     }
-    const size_t need = (size_t)S * gp->chunk * Np;
-    if (g.cand_planes_bytes < need) {
-        cudaFree(g.cand_planes);
-        g.cand_planes = nullptr; g.cand_planes_bytes = 0;
-        CUDA_TRY(cudaMalloc(&g.cand_planes, need));
-        g.cand_planes_bytes = need;
-    }
+    int rcp = ensure_cand_planes((size_t)S * gp->chunk * Np);
+    if (rcp) return rcp;
     // covariance entries lie in [0, sigma^2]: one global exponent for the candidate side
     const int fexp = oz::scale_exponent(gp->cov);
-    ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)mc_pad * Np * (8.0 + S));
-    oz::launch_slice<S>(gp->KcT, Np, mc_pad, Np, nullptr, fexp, 0, g.cand_planes, g.stream);
-    prof_end(m);
-    LAUNCH_CHECK("ozaki slice candidates");
+    ProfMark m{};
+    if (!sliced) {
+        m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)mc_pad * Np * (8.0 + S));
+        oz::launch_slice<S>(gp->KcT, Np, mc_pad, Np, nullptr, fexp, 0, g.cand_planes, g.stream);
+        prof_end(m);
+        LAUNCH_CHECK("ozaki slice candidates");
+    }
     // flops: FP64-equivalent Np^2 Mc; bytes field carries the int8 operations actually issued
     m = prof_begin(EXQ_PROF_GEMM_PREDICT, (double)Np * Np * mc_pad,
                    (double)Np * (Np + oz::BLK_R) * mc_pad * (S * (S + 1) / 2));
@@ -775,12 +789,35 @@ int variance_digits(const exq_gp_t gp) {
     if (g.oz_slices < 7 && gp->kappa >= g.guard_widen) return 7;
     return g.oz_slices;
 }
-int variance_ozaki(exq_gp_t gp, int mc_pad, int digits) {
+int variance_ozaki(exq_gp_t gp, int mc_pad, int digits, bool sliced = false) {
     switch (digits) {
-        case 5: return variance_ozaki_s<5>(gp, mc_pad);
-        case 7: return variance_ozaki_s<7>(gp, mc_pad);
-        default: return variance_ozaki_s<6>(gp, mc_pad);
+        case 5: return variance_ozaki_s<5>(gp, mc_pad, sliced);
+        case 7: return variance_ozaki_s<7>(gp, mc_pad, sliced);
+        default: return variance_ozaki_s<6>(gp, mc_pad, sliced);
     }
+}
+
+// fused cross-covariance assembly: digit planes + partial means / repulsion products, no FP64 chunk (pei_fused.cuh)
+template <int KID, int S>
+int launch_assemble_digits(const AsmDigArgs& a) {
+    const size_t smem = ((size_t)(128 + ASM_BN) * a.d + (size_t)a.d * ASM_XT_LD + a.d + 2 + ASM_BN) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(assemble_digits_kernel<KID, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    dim3 grid(a.Np / ASM_BN, a.mc_pad / 128, 1);
+    const double entries = (double)a.mc_pad * a.Np;
+    ProfMark m = prof_begin(EXQ_PROF_ASSEMBLE, entries * (3.0 * a.d + 30.0), entries * S);
+    assemble_digits_kernel<KID, S><<<grid, ASM_THREADS, smem, g.stream>>>(a);
+    prof_end(m);
+    return check_launch("assemble_digits_kernel");
+}
+template <int S>
+int launch_assemble_digits_k(const AsmDigArgs& a) {
+    if (a.kernel_id == EXQ_KERNEL_MATERN52) return launch_assemble_digits<EXQ_KERNEL_MATERN52, S>(a);
+    if (a.kernel_id == EXQ_KERNEL_SQEXP) return launch_assemble_digits<EXQ_KERNEL_SQEXP, S>(a);
+    return launch_assemble_digits<EXQ_KERNEL_PRODMAT52, S>(a);
 }
 
 // mean / var / (pei) of the fitted GP at device-resident candidates Xc[Mpad][d]
@@ -788,15 +825,53 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
                    double tmax, int want_pei, double* mean, double* var, double* pei) {
     const int Np = gp->Np;
     int64_t chunk = default_chunk(gp, Mpad);
-    int rc = ensure_pred_scratch(gp, chunk);
-    if (rc) return rc;
     // int8 digits bound |D_t| <= S 2^14 K < 2^31 only up to K = 16384
     const int vdigits = variance_digits(gp);
     const bool use_oz = vdigits > 0;
     if (use_oz && vdigits != g.oz_slices && Mpad > 8) g.guard_widened++;
+    const bool fused_pei = g.pei_fused && use_oz && g.fast_corr && (vdigits == 6 || vdigits == 7);
+    int rc = ensure_pred_scratch(gp, chunk, fused_pei ? 128 : -1);
+    if (rc) return rc;
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc_pad = std::min(chunk, Mpad - c0);
         const int64_t mc = std::min(mc_pad, M - c0);
+        if (fused_pei && mc > 8) {
+            const int nM = Np / ASM_BN;
+            const size_t need = (size_t)2 * nM * chunk;
+            if (g.pmr_elems < need) {
+                cudaFree(g.PMR);
+                g.PMR = nullptr; g.pmr_elems = 0;
+                CUDA_TRY(cudaMalloc(&g.PMR, need * sizeof(double)));
+                g.pmr_elems = need;
+            }
+            if ((rc = ensure_cand_planes((size_t)vdigits * gp->chunk * Np))) return rc;
+            AsmDigArgs ad{};
+            ad.Xc = Xc + c0 * gp->d; ad.X = gp->X; ad.theta = gp->fit.theta; ad.alpha = gp->fit.alpha;
+            ad.planes = g.cand_planes; ad.PM = g.PMR; ad.PR = g.PMR + (size_t)nM * chunk; ad.ldp = mc_pad;
+            ad.mc_pad = (int)mc_pad; ad.m_valid = (int)mc; ad.N = (int)gp->N; ad.Np = Np; ad.d = gp->d;
+            ad.kernel_id = gp->kernel_id; ad.cand_exp = oz::scale_exponent(gp->cov);
+            rc = (vdigits == 7) ? launch_assemble_digits_k<7>(ad) : launch_assemble_digits_k<6>(ad);
+            if (rc) return rc;
+            if ((rc = variance_ozaki(gp, (int)mc_pad, vdigits, /*sliced=*/true))) return rc;
+            FinLightArgs f{};
+            f.PM = ad.PM; f.PR = ad.PR; f.P = gp->P; f.ldp = mc_pad; f.nM = nM; f.nP = 2 * (Np / oz::BLK_R);
+            f.theta = gp->fit.theta; f.Xc = Xc + c0 * gp->d; f.Rp = rep; f.n_rep = n_rep; f.d = gp->d;
+            f.kernel_id = gp->kernel_id; f.m_valid = (int)mc; f.tmax = tmax; f.want_pei = want_pei;
+            f.mean = mean ? mean + c0 : nullptr; f.var = var ? var + c0 : nullptr; f.pei = pei ? pei + c0 : nullptr;
+            const size_t rp_bytes = (size_t)n_rep * gp->d * sizeof(double);
+            f.rp_in_smem = (want_pei && rp_bytes <= 160 * 1024) ? 1 : 0;
+            const size_t fsmem = (gp->d + 2) * sizeof(double) + (f.rp_in_smem ? rp_bytes : 0);
+            static bool fl_attr = false;
+            if (!fl_attr) {
+                CUDA_TRY(cudaFuncSetAttribute(fin_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                fl_attr = true;
+            }
+            ProfMark mf = prof_begin(EXQ_PROF_STREAM, (double)mc * n_rep * (3.0 * gp->d + 30.0), (double)mc * (2.0 * nM + f.nP) * 8.0);
+            fin_light_kernel<<<(unsigned)((mc + 127) / 128), 128, fsmem, g.stream>>>(f);
+            prof_end(mf);
+            LAUNCH_CHECK("fin_light_kernel");
+            continue;
+        }
         AsmArgs a{};
         a.Xi = Xc + c0 * gp->d; a.Xj = gp->X; a.theta = gp->fit.theta; a.out = gp->KcT;
         a.ld = Np; a.n_i = (int)mc; a.n_j = (int)gp->N; a.d = gp->d; a.kernel_id = gp->kernel_id;
@@ -1008,6 +1083,7 @@ int exq_init(int device) {
     }
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_PEI_FUSED")) g.pei_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_FUSE_N")) { const int v = atoi(e); g.fuse_n = (v >= 256 && v <= 1024) ? (v / 128) * 128 : 0; }
     if (const char* e = getenv("EXQ_FUSE_G")) { const int v = atoi(e); g.fuse_g = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : 0; }
     if (const char* e = getenv("EXQ_REFINE_STEPS")) g.refine_steps = std::max(0, std::min(4, atoi(e)));
@@ -1033,7 +1109,7 @@ int exq_shutdown(void) {
     cudaStreamSynchronize(g.stream);
     sys_pool_clear();
     if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
-    cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes);
+    cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes); cudaFree(g.PMR);
     plane_pool_clear();
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();
@@ -1085,6 +1161,11 @@ int exq_set_fused(int max_rows, int cluster_ctas) {
         return fail(EXQ_ERR_ARG, "exq_set_fused: cluster_ctas must be 0 (automatic), 1, 2, 4, 8 or 16");
     g.fuse_n = max_rows;
     g.fuse_g = cluster_ctas;
+    return EXQ_OK;
+}
+int exq_set_pei_fused(int on) {
+    REQUIRE_READY();
+    g.pei_fused = on != 0;
     return EXQ_OK;
 }
 int exq_set_refine_steps(int steps) {

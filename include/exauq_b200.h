@@ -82,6 +82,12 @@ int exq_set_refine_steps(int steps);
  * thread-block cluster of cluster_ctas CTAs per system (0 = automatic: 16 for up to 8 systems, else 8).
  * EXQ_FUSE_N / EXQ_FUSE_G.  Same arithmetic either way (FP64 DMMA): used by tests to compare the two paths. */
 int exq_set_fused(int max_rows, int cluster_ctas);
+/* Prediction / PEI pipeline over candidate chunks (csrc/pei_fused.cuh).  on (default): the cross-covariance tile
+ * kernel writes the int8 digit planes of the variance product directly and accumulates the mean and the repulsion
+ * product per tile -- the FP64 covariance chunk is never materialised.  off: round 1's three passes (FP64 chunk,
+ * slicer, per-candidate epilogue).  EXQ_PEI_FUSED.  Same quantities either way (mogp GaussianProcess.predict,
+ * exauq/core/emulators.py:649; PEICalculator.compute, exauq/core/designers.py:522-706). */
+int exq_set_pei_fused(int on);
 /* current max_rows and how many clusters of 8 / 16 CTAs of that kernel the device co-schedules */
 int exq_fused_info(int* max_rows, int* clusters8, int* clusters16);
 /* kappa of the last exq_gp_fit of this handle and whether the guard sent that fit to FP64 DMMA */

@@ -84,3 +84,45 @@ def test_fused_against_oracle(exq, orc):
     assert info[0] == 0 and abs(val[0] - oval) <= 1e-9 * abs(oval)
     assert np.all(np.abs(grad[0] - ograd) <= 1e-7 * np.max(np.abs(ograd)))
     dev.close()
+
+
+@pytest.mark.parametrize("kernel,N,d,M,ell,nug", [("Matern52", 1500, 4, 5000, 0.45, 1e-9), ("SquaredExponential", 700, 3, 3001, 0.15, 1e-6),
+                                                  ("ProductMat52", 300, 2, 777, 0.45, 1e-9), ("Matern52", 4096, 8, 40000, 0.45, 1e-9)])
+def test_fused_pei_pipeline_equals_three_pass_pipeline_and_oracle(exq, orc, kernel, N, d, M, ell, nug):
+    """csrc/pei_fused.cuh (assembly -> digit planes + per-tile mean / repulsion partials, no FP64 covariance chunk)
+    against round 1's three passes on the same inputs -- identical digits, so identical variances; means and PEI
+    differ only by summation order -- and both against the oracle's PEI (exauq/core/designers.py:522-706)."""
+    lib = exq._lib
+    X, y = orc.synthetic_problem(N, d)
+    Xc = orc.synthetic_candidates(M, d)
+    raw = np.full(d, -2 * np.log(ell))
+    rep = np.random.default_rng(1).uniform(0, 1, (2 * d + 2 ** d, d))
+    dev = exq.DeviceGP(X, y, kernel).fit(raw, 1.7, nug)
+    out = {}
+    for mode in (False, True):
+        lib.set_pei_fused(mode)
+        m, v = dev.predict(Xc)
+        cand = exq.DeviceCandidates(Xc)
+        cand.pei_eval(dev, rep, float(y.max()))
+        idx, val = cand.batch(dev, 5)
+        out[mode] = (m, v, cand.download("pei"), idx, val)
+        cand.close()
+    lib.set_pei_fused(True)
+    # same digits -> same partial sums of squares; only the order in which the Np/32 partials are added differs
+    assert np.allclose(out[True][1], out[False][1], rtol=0, atol=1e-13 * 1.7)
+    # means: sums of N terms k_cj alpha_j in a different order -> a few ulp of sum_j |k_cj alpha_j| <= 1.7 |alpha|_1
+    K = 1.7 * lib.corr(kernel, raw, X, X) + nug * np.eye(N)
+    a1 = float(np.abs(np.linalg.solve(K, y)).sum()) * 1.7
+    assert np.all(np.abs(out[True][0] - out[False][0]) <= 1e-14 * a1)
+    pmax = float(out[False][2].max())
+    assert np.allclose(out[True][2], out[False][2], rtol=1e-6, atol=1e-12 * pmax)   # EI amplifies the mean's last bits
+    assert out[True][3].tolist() == out[False][3].tolist()
+    if N <= 1500:
+        ref = orc.fit(X, y, kernel, raw, 1.7, nug)
+        mo, vo = orc.predict(ref, Xc)
+        assert np.all(np.abs(out[True][0] - mo) <= np.maximum(1e-8 * np.abs(mo), 1e-9))
+        assert np.all(np.abs(out[True][1] - vo) <= np.maximum(1e-8 * np.abs(vo), 1e-9))
+        oi, ov, _ = orc.pei_batch_argmax(ref, kernel, Xc, rep, float(y.max()), 5)
+        assert out[True][3].tolist() == oi.tolist()
+        assert np.allclose(out[True][4], ov, rtol=1e-6)
+    dev.close()
