@@ -51,6 +51,8 @@ SIGNATURES = {
     "exq_gp_create": (C.c_int, [C.c_int64, C.c_int, _dp, _dp, C.c_int, C.POINTER(_vp)]),
     "exq_gp_destroy": (C.c_int, [_vp]),
     "exq_gp_fit": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]),
+    "exq_gp_pivot_order": (C.c_int, [_vp, _dp, C.c_double, _ip, _ip]),
+    "exq_gp_fit_pivoted": (C.c_int, [_vp, _dp, C.c_double, C.c_int, _dp, _dp]),
     "exq_gp_predict": (C.c_int, [_vp, _dp, C.c_int64, _dp, _dp]),
     "exq_gp_cross_cov": (C.c_int, [_vp, _dp, C.c_int64, _dp]),
     "exq_gp_loo": (C.c_int, [_vp, _dp, _dp, _dp]),
@@ -196,6 +198,26 @@ class DeviceGP:
         self.nugget_used, self.logdet, self.quad = nu.value, ld.value, q.value
         return self
 
+    def pivot_order(self, corr_raw, cov: float):
+        """(piv, rank) of the pivoted Cholesky factorisation of cov * C(X, X) (LAPACK dpstrf's pivot rule and
+        stopping tolerance; nugget = "pivot").  Leaves the handle unfitted."""
+        corr_raw = as_f64(corr_raw).reshape(self.d)
+        piv = np.zeros(self.N, dtype=np.int32)
+        rank = C.c_int()
+        check(load().exq_gp_pivot_order(self._h, _d(corr_raw), float(cov), piv.ctypes.data_as(_ip), C.byref(rank)),
+              "exq_gp_pivot_order")
+        return piv, int(rank.value)
+
+    def fit_pivoted(self, corr_raw, cov: float, rank: int):
+        """Fit a handle whose data are already in pivot order: factor of the leading ``rank`` columns, mogp's
+        decreasing diagonal for the rest (nugget = "pivot", rank-deficient or ill-conditioned case)."""
+        corr_raw = as_f64(corr_raw).reshape(self.d)
+        ld, q = C.c_double(), C.c_double()
+        check(load().exq_gp_fit_pivoted(self._h, _d(corr_raw), float(cov), int(rank), C.byref(ld), C.byref(q)),
+              "exq_gp_fit_pivoted")
+        self.nugget_used, self.logdet, self.quad = 0.0, ld.value, q.value
+        return self
+
     def kappa(self):
         """(kappa, on_fp64): the conditioning proxy (max L_ii / min L_ii)^2 of the last fit and whether the
         int8 guard sent that fit to the FP64 DMMA path."""
@@ -253,6 +275,95 @@ class DeviceGP:
                                           _d(grad) if want_grad else None, info.ctypes.data_as(_ip), _d(nug)),
               "exq_gp_logpost_batch")
         return val, grad, info, nug
+
+
+class PivotedDeviceGP:
+    """nugget = "pivot" (mogp GaussianProcess.fit -> pivot_cholesky; exauq/core/emulators.py:129-137): the
+    covariance matrix is factored with diagonal pivoting on the device, the training data are then held in pivot
+    order so that the factor and its inverse stay triangular for every downstream kernel, and everything indexed by
+    training point (LOO sweep, kinv, cross-covariances) is handed back in the caller's order.  Same methods as
+    ``DeviceGP``; ``rank`` is the numerical rank LAPACK's stopping rule finds."""
+
+    def __init__(self, X, y, kernel: str):
+        self.base = DeviceGP(X, y, kernel)          # caller's order: pivot search, hyperparameter estimation
+        self.X, self.y, self.N, self.d, self.kernel = self.base.X, self.base.y, self.base.N, self.base.d, kernel
+        self.dev: Optional[DeviceGP] = None
+        self.piv = np.arange(self.N, dtype=np.int32)
+        self.rank = self.N
+        self.nugget_used = None
+
+    @property
+    def _h(self):
+        return self.dev._h
+
+    def close(self):
+        self.base.close()
+        if self.dev is not None:
+            self.dev.close()
+
+    def fit(self, corr_raw, cov: float, nugget: float = 0.0, adaptive: bool = False):
+        piv, rank = self.base.pivot_order(corr_raw, cov)
+        if rank < 1:
+            raise NotPositiveDefiniteError("pivoted Cholesky: no positive diagonal entry")
+        if self.dev is not None:
+            self.dev.close()
+        self.piv, self.rank = piv, rank
+        self.dev = DeviceGP(self.X[piv], self.y[piv], self.kernel)
+        done = False
+        if rank == self.N:
+            try:                                     # full rank: the fast recursion on the permuted matrix is the
+                self.dev.fit(corr_raw, cov, 0.0, False)   # pivoted factor (same column order, no interchanges left)
+                done = True
+            except NotPositiveDefiniteError:
+                pass
+        if not done:
+            self.dev.fit_pivoted(corr_raw, cov, rank)
+        self.nugget_used, self.logdet, self.quad = None, self.dev.logdet, self.dev.quad
+        return self
+
+    @property
+    def neg_log_likelihood(self) -> float:
+        return self.dev.neg_log_likelihood
+
+    def kappa(self):
+        return self.dev.kappa()
+
+    def predict(self, Xc):
+        return self.dev.predict(Xc)
+
+    def cross_cov(self, Xq) -> np.ndarray:
+        out = np.empty((np.asarray(Xq).reshape(-1, self.d).shape[0], self.N))
+        out[:, self.piv] = self.dev.cross_cov(Xq)
+        return out
+
+    def _unpermute(self, *vs):
+        outs = []
+        for v in vs:
+            o = np.empty_like(v)
+            o[self.piv] = v
+            outs.append(o)
+        return tuple(outs)
+
+    def loo(self):
+        return self._unpermute(*self.dev.loo())
+
+    def loo_refit(self, idx):
+        inv = np.empty(self.N, dtype=np.int32)
+        inv[self.piv] = np.arange(self.N, dtype=np.int32)
+        return self.dev.loo_refit(inv[np.asarray(idx, dtype=np.int64)])
+
+    def kinv(self) -> np.ndarray:
+        out = np.empty((self.N, self.N))
+        out[np.ix_(self.piv, self.piv)] = self.dev.kinv()
+        return out
+
+    def logpost_batch(self, theta_raw, nugget: float = 0.0, adaptive: bool = False, want_grad: bool = True,
+                      fit_nugget: bool = False):
+        """Objective / gradient of hyperparameter estimation: a covariance matrix that is numerically of full rank has
+        the same log-posterior with or without pivoting, so the batched recursion (nugget 0, no jitter) is used;
+        a matrix it cannot factor is reported through ``info`` (restart skipped), where mogp would continue on its
+        rank-deficient surrogate factor."""
+        return self.base.logpost_batch(theta_raw, 0.0, False, want_grad, False)
 
 
 class DeviceCandidates:

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libexauq_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "exq_api.cu")]
 HEADERS = [
     os.path.join(HERE, "csrc", n)
-    for n in ("exq_common.cuh", "gemm_dmma.cuh", "leaf.cuh", "kernels.cuh", "ozaki_i8.cuh", "ozaki_gemm.cuh", "fused_node.cuh", "pei_fused.cuh")
+    for n in ("exq_common.cuh", "gemm_dmma.cuh", "leaf.cuh", "kernels.cuh", "ozaki_i8.cuh", "ozaki_gemm.cuh", "fused_node.cuh", "pei_fused.cuh", "pivot.cuh")
 ] + [os.path.join(os.path.dirname(HERE), "include", "exauq_b200.h")]
 
 NVCC_FLAGS = [

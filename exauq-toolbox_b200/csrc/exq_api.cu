@@ -22,6 +22,7 @@
 #include "ozaki_i8.cuh"
 #include "ozaki_gemm.cuh"
 #include "pei_fused.cuh"
+#include "pivot.cuh"
 
 using namespace exq;
 
@@ -1388,6 +1389,110 @@ int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, i
     gp->nugget = nug;
     gp->corr_raw.assign(corr_raw, corr_raw + d);
     if (nugget_used) *nugget_used = nug;
+    if (logdet) *logdet = ldq[0];
+    if (quad) *quad = ldq[1];
+    return EXQ_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// nugget = "pivot" (pivot.cuh)
+// -------------------------------------------------------------------------------------
+namespace {
+struct PivScratch {
+    int *piv = nullptr, *rank = nullptr, *cand_i = nullptr;
+    double* cand_v = nullptr;
+    int blocks = 0;
+    ~PivScratch() { cudaFree(piv); cudaFree(rank); cudaFree(cand_i); cudaFree(cand_v); }
+};
+
+// K (nugget-free, lower) of the handle's data into gp->fit.A, then the pivoted (pivoting = 1) or plain left-looking
+// (pivoting = 0, first stop_at columns) Cholesky kernel; rank and, if wanted, the pivot order come back to the host
+int pivot_factor(exq_gp_t gp, const double* corr_raw, double cov, int pivoting, int stop_at, PivScratch& sc,
+                 int* rank_host, int* piv_host) {
+    const int N = (int)gp->N, d = gp->d;
+    if ((size_t)N * sizeof(double) > 200 * 1024) return fail(EXQ_ERR_ARG, "nugget = 'pivot': N <= 25600 on this backend");
+    int rc = sys_alloc(gp->fit, 1, N, d, false, false);
+    if (rc) return rc;
+    Sys& s = gp->fit;
+    std::vector<double> th(d + 2);
+    for (int k = 0; k < d; k++) {
+        th[k] = exp(corr_raw[k]);
+        if (!isfinite(th[k])) return fail(EXQ_ERR_ARG, "pivot: overflow in exp(corr_raw)");
+    }
+    th[d] = cov; th[d + 1] = 0.0;
+    if ((rc = upload_theta(s, th))) return rc;
+    if ((rc = assemble_sym(s, gp->X, 0, N, gp->kernel_id))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(pivot_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(trtri_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    const size_t smem = (size_t)N * sizeof(double);
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pivot_chol_kernel, PIV_THREADS, smem));
+    if (per_sm < 1) return fail(EXQ_ERR_CUDA, "pivot_chol_kernel does not fit an SM");
+    sc.blocks = g.sm_count * std::min(per_sm, 2);
+    CUDA_TRY(cudaMalloc(&sc.piv, (size_t)N * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&sc.rank, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&sc.cand_i, (size_t)sc.blocks * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&sc.cand_v, (size_t)sc.blocks * sizeof(double)));
+    PivArgs a{};
+    a.A = s.A; a.ld = s.Np; a.n = N; a.pivoting = pivoting; a.stop_at = stop_at;
+    a.dots = s.tvec; a.work = s.kvec; a.piv = sc.piv; a.rank = sc.rank; a.cand_v = sc.cand_v; a.cand_i = sc.cand_i;
+    void* args[] = {&a};
+    ProfMark m = prof_begin(EXQ_PROF_LEAF, (double)N * N * N / 3.0, 0.0);
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)pivot_chol_kernel, dim3(sc.blocks), dim3(PIV_THREADS), args, smem, g.stream));
+    prof_end(m);
+    LAUNCH_CHECK("pivot_chol_kernel");
+    CUDA_TRY(cudaMemcpyAsync(rank_host, sc.rank, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    if (piv_host) CUDA_TRY(cudaMemcpyAsync(piv_host, sc.piv, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return EXQ_OK;
+}
+}  // namespace
+
+int exq_gp_pivot_order(exq_gp_t gp, const double* corr_raw, double cov, int* piv, int* rank) {
+    REQUIRE_READY();
+    if (!gp || !corr_raw || !(cov > 0.0) || !piv || !rank) return fail(EXQ_ERR_ARG, "exq_gp_pivot_order: bad argument");
+    gp->fitted = false;      // the workspace of the fit is used as scratch
+    gp->planes_S = 0;
+    PivScratch sc;
+    return pivot_factor(gp, corr_raw, cov, 1, 0, sc, rank, piv);
+}
+
+int exq_gp_fit_pivoted(exq_gp_t gp, const double* corr_raw, double cov, int rank, double* logdet, double* quad) {
+    REQUIRE_READY();
+    if (!gp || !corr_raw || !(cov > 0.0) || rank < 1 || rank > gp->N)
+        return fail(EXQ_ERR_ARG, "exq_gp_fit_pivoted: bad argument");
+    const int N = (int)gp->N;
+    gp->fitted = false;
+    gp->planes_S = 0;
+    PivScratch sc;
+    int got = 0;
+    int rc = pivot_factor(gp, corr_raw, cov, 0, rank, sc, &got, nullptr);
+    if (rc) return rc;
+    if (got != rank) return fail(EXQ_NOT_PD, "exq_gp_fit_pivoted: non-positive pivot inside the stated rank");
+    Sys& s = gp->fit;
+    pivot_fill_kernel<<<N, 128, 0, g.stream>>>(s.A, s.Np, N, sc.rank);
+    LAUNCH_CHECK("pivot_fill_kernel");
+    CUDA_TRY(cudaMemsetAsync(s.Linv, 0, (size_t)s.sq() * sizeof(double), g.stream));
+    ProfMark m = prof_begin(EXQ_PROF_LEAF, (double)N * N * N / 3.0, 0.0);
+    trtri_lower_kernel<<<s.Np, 128, (size_t)N * sizeof(double), g.stream>>>(s.A, s.Linv, s.Np, N, s.Np);
+    prof_end(m);
+    LAUNCH_CHECK("trtri_lower_kernel");
+    CUDA_TRY(cudaMemsetAsync(s.info, 0, sizeof(int), g.stream));
+    if ((rc = solve_vectors(s, gp->y, 0, N))) return rc;
+    double ldq[2], dst[2];
+    CUDA_TRY(cudaMemcpyAsync(ldq, s.ldq, sizeof(ldq), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(dst, s.dstat, sizeof(dst), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    gp->kappa = (dst[0] > 0.0) ? (dst[1] / dst[0]) * (dst[1] / dst[0]) : INFINITY;
+    gp->fit_on_dmma = true;
+    gp->fitted = true;
+    gp->cov = cov;
+    gp->nugget = 0.0;
+    gp->corr_raw.assign(corr_raw, corr_raw + gp->d);
     if (logdet) *logdet = ldq[0];
     if (quad) *quad = ldq[1];
     return EXQ_OK;

@@ -37,8 +37,8 @@ from scipy.linalg import LinAlgError
 from scipy.optimize import minimize
 
 from . import _lib
-from ._lib import DeviceCandidates, DeviceGP
-from .priors import MapPriors
+from ._lib import DeviceCandidates, DeviceGP, PivotedDeviceGP
+from .priors import MapPriors, make_priors
 from .refapi import (
     AbstractGaussianProcess,
     GaussianProcessHyperparameters,
@@ -143,13 +143,17 @@ class B200GaussianProcess(AbstractGaussianProcess):
         Covariance function (default "SquaredExponential", as ``MogpEmulator``).
     nugget : {"adaptive", "fit", "pivot"} or float
         Nugget handling (default "adaptive": 0 unless the Cholesky factorisation fails).
-        "pivot" is not available on this backend.
+        "pivot": no nugget, pivoted Cholesky factorisation (mogp ``pivot_cholesky`` / LAPACK ``dpstrf``) that
+        tolerates a numerically rank-deficient covariance matrix.
     n_tries : int
         Number of L-BFGS-B restarts in hyperparameter estimation (mogp default 15).
     **kwargs :
-        ``inputs`` / ``targets`` are ignored as in ``MogpEmulator``; ``mean=None``,
-        ``priors=None``, ``inputdict``, ``use_patsy`` are accepted; anything else raises
-        ``RuntimeError`` (exauq/core/emulators.py:175-190).
+        ``inputs`` / ``targets`` are ignored as in ``MogpEmulator``; ``priors`` may be ``None`` (mogp's data-driven
+        defaults), a ``GPPriors``-like object (``exauq_toolbox_b200.priors.GPPriors`` or mogp's own) or a dict with
+        ``corr`` / ``cov`` / ``nugget`` entries; ``mean=None``, ``inputdict``, ``use_patsy`` are accepted; anything
+        else -- including a non-zero mean function, which the designers do not support
+        (docs/designers/tutorials/training_gp_tutorial.md:146-148) -- raises ``RuntimeError``
+        (exauq/core/emulators.py:175-190).
     """
 
     def __init__(self, **kwargs):
@@ -169,11 +173,22 @@ class B200GaussianProcess(AbstractGaussianProcess):
         bad_nugget = (isinstance(nugget, str) and nugget not in ("adaptive", "fit", "pivot")) or (
             not isinstance(nugget, str) and (not isinstance(nugget, Real) or nugget < 0)
         )
-        if kwargs or mean is not None or priors is not None or bad_nugget or nugget == "pivot":
+        if kwargs or mean is not None or bad_nugget:
             raise RuntimeError(
                 f"Could not construct the device Gaussian process during initialisation of "
                 f"{self.__class__.__name__}"
             )
+        if priors is not None:
+            try:                     # shape is checked against the data at fit time
+                ok = isinstance(priors, dict) or (hasattr(priors, "corr") and hasattr(priors, "cov"))
+            except Exception:
+                ok = False
+            if not ok:
+                raise RuntimeError(
+                    f"Could not construct the device Gaussian process during initialisation of "
+                    f"{self.__class__.__name__}"
+                )
+        self._priors = priors
         self._kernel_name = kernel
         self._nugget = nugget
         self._state: Optional[_FitState | _LooView] = None
@@ -290,7 +305,7 @@ class B200GaussianProcess(AbstractGaussianProcess):
             return float(hp.nugget), False
         if isinstance(self._nugget, Real):
             return float(self._nugget), False
-        return 0.0, True  # "adaptive"
+        return 0.0, True  # "adaptive" ("pivot" is dispatched before this is used)
 
     def _fit_with_hyperparameters(self, training_data, X, y, hp) -> _FitState:
         if len(hp.corr_length_scales) != X.shape[1]:
@@ -299,12 +314,13 @@ class B200GaussianProcess(AbstractGaussianProcess):
             )
         corr_raw = np.array([GaussianProcessHyperparameters.transform_corr(c) for c in hp.corr_length_scales])
         nugget, adaptive = self._nugget_args(hp)
-        dev = DeviceGP(X, y, self._kernel_name)
+        pivot = self._nugget == "pivot"          # only when no numeric nugget was supplied (emulators.py:427-445)
+        dev = PivotedDeviceGP(X, y, self._kernel_name) if pivot else DeviceGP(X, y, self._kernel_name)
         dev.fit(corr_raw, float(hp.process_var), nugget, adaptive)
         fitted = GaussianProcessHyperparameters(
             corr_length_scales=np.array(hp.corr_length_scales, dtype=float),
             process_var=float(hp.process_var),
-            nugget=float(dev.nugget_used),
+            nugget=None if pivot else float(dev.nugget_used),      # mogp leaves theta.nugget unset for "pivot"
         )
         return _FitState(training_data, X, y, self._kernel_name, fitted, corr_raw, dev)
 
@@ -317,8 +333,9 @@ class B200GaussianProcess(AbstractGaussianProcess):
         fit_nugget = self._nugget == "fit"
         if fit_nugget and raw_bounds is not None:
             raw_bounds = tuple(raw_bounds) + ((None, None),)      # the nugget itself is unbounded
-        dev = DeviceGP(X, y, self._kernel_name)
-        priors = MapPriors(X, fit_nugget=fit_nugget)
+        pivot = self._nugget == "pivot"
+        dev = PivotedDeviceGP(X, y, self._kernel_name) if pivot else DeviceGP(X, y, self._kernel_name)
+        priors = make_priors(self._priors, X, fit_nugget=fit_nugget)
         nugget = 0.0 if isinstance(self._nugget, str) else float(self._nugget)
         adaptive = self._nugget == "adaptive"
         starts = [priors.sample() for _ in range(self._n_tries)]
@@ -333,7 +350,7 @@ class B200GaussianProcess(AbstractGaussianProcess):
         fitted = GaussianProcessHyperparameters(
             corr_length_scales=np.exp(-0.5 * theta[:d]),
             process_var=float(np.exp(theta[d])),
-            nugget=float(dev.nugget_used),
+            nugget=None if pivot else float(dev.nugget_used),
         )
         return _FitState(training_data, X, y, self._kernel_name, fitted, np.array(theta[:d]), dev)
 
@@ -515,7 +532,7 @@ class B200GaussianProcess(AbstractGaussianProcess):
         nugget = 0.0 if isinstance(self._nugget, str) else float(self._nugget)
         val, grad, info, _ = st.dev.logpost_batch(theta_raw, nugget, isinstance(self._nugget, str))
         if with_prior:
-            pri = MapPriors(st.X)
+            pri = make_priors(self._priors, st.X)
             for r in range(theta_raw.shape[0]):
                 val[r] -= pri.logp(theta_raw[r])
                 grad[r] -= pri.dlogp_draw(theta_raw[r])

@@ -51,6 +51,169 @@ def _solve_invgamma(lo: float, hi: float) -> Optional[tuple[float, float]]:
     return float(np.exp(sol["x"][0])), float(np.exp(sol["x"][1]))
 
 
+# ---------------------------------------------------------------------------------------------------
+# user-supplied priors (the ``priors=`` keyword MogpEmulator passes through, exauq/core/emulators.py:129-137)
+# ---------------------------------------------------------------------------------------------------
+class WeakPrior:
+    """Improper flat prior (mogp ``WeakPrior``): contributes nothing; starting points from U(-2.5, 2.5) on the
+    raw scale."""
+
+    def logp(self, x):
+        return 0.0
+
+    def dlogpdx(self, x):
+        return 0.0
+
+
+class InvGammaPrior(WeakPrior):
+    """Inverse-gamma density on the linear-scale parameter (mogp ``InvGammaPrior(shape, scale)``)."""
+
+    def __init__(self, shape, scale):
+        if not (shape > 0.0 and scale > 0.0):
+            raise ValueError("shape and scale must be positive")
+        self.shape, self.scale = float(shape), float(scale)
+
+    def logp(self, x):
+        return float(self.shape * np.log(self.scale) - gammaln(self.shape) - (self.shape + 1.0) * np.log(x) - self.scale / x)
+
+    def dlogpdx(self, x):
+        return float(-(self.shape + 1.0) / x + self.scale / x**2)
+
+    def sample_x(self):
+        return float(scipy.stats.invgamma.rvs(self.shape, scale=self.scale))
+
+
+class GammaPrior(InvGammaPrior):
+    """Gamma density (mogp ``GammaPrior(shape, scale)``)."""
+
+    def logp(self, x):
+        return float(-self.shape * np.log(self.scale) - gammaln(self.shape) + (self.shape - 1.0) * np.log(x) - x / self.scale)
+
+    def dlogpdx(self, x):
+        return float((self.shape - 1.0) / x - 1.0 / self.scale)
+
+    def sample_x(self):
+        return float(scipy.stats.gamma.rvs(self.shape, scale=self.scale))
+
+
+class LogNormalPrior(InvGammaPrior):
+    """Log-normal density (mogp ``LogNormalPrior(shape, scale)``: shape = sigma of ln x, scale = exp(mean of ln x))."""
+
+    def logp(self, x):
+        return float(-0.5 * (np.log(x / self.scale) / self.shape) ** 2 - 0.5 * np.log(2.0 * np.pi) - np.log(x)
+                     - np.log(self.shape))
+
+    def dlogpdx(self, x):
+        return float(-np.log(x / self.scale) / self.shape**2 / x - 1.0 / x)
+
+    def sample_x(self):
+        return float(scipy.stats.lognorm.rvs(self.shape, scale=self.scale))
+
+
+class GPPriors:
+    """Container mirroring mogp ``GPPriors(corr=..., cov=..., nugget=...)`` for the zero-mean case: one prior per
+    correlation length, one on the process variance, one on the nugget (used only when the nugget is fitted).
+    ``None`` entries are flat priors."""
+
+    def __init__(self, corr=None, cov=None, nugget=None, n_corr=None, nugget_type="fit", mean=None):
+        if mean is not None:
+            raise ValueError("mean-function priors are not supported: the designers assume a zero mean")
+        if corr is None:
+            if n_corr is None:
+                raise ValueError("n_corr is needed when no correlation-length priors are given")
+            corr = [None] * int(n_corr)
+        self.corr = [WeakPrior() if c is None else c for c in corr]
+        self.cov = WeakPrior() if cov is None else cov
+        self.nugget = WeakPrior() if nugget is None else nugget
+        self.nugget_type = nugget_type
+
+    @property
+    def n_corr(self):
+        return len(self.corr)
+
+
+def _is_flat(dist) -> bool:
+    return dist is None or not hasattr(dist, "sample_x")
+
+
+class CustomMapPriors:
+    """User-supplied priors behind the interface the MAP driver uses (``logp``, ``dlogp_draw``, ``sample``): any
+    object with ``corr`` (sequence), ``cov`` and ``nugget`` attributes whose entries offer ``logp(x)`` /
+    ``dlogpdx(x)`` / ``sample_x()`` on the linear-scale parameter -- this module's classes or mogp's own -- or a dict
+    with those keys.  Densities act on the linear scale without a Jacobian term and starting points are drawn
+    in parameter order through numpy's global RNG, exactly as for the default priors."""
+
+    def __init__(self, priors, d: int, fit_nugget: bool = False):
+        if isinstance(priors, dict):
+            extra = set(priors) - {"corr", "cov", "nugget", "n_corr", "nugget_type", "mean"}
+            if extra:
+                raise ValueError(f"unknown prior specification keys: {sorted(extra)}")
+            kw = dict(priors)
+            kw.setdefault("n_corr", d)
+            priors = GPPriors(**kw)
+        if not (hasattr(priors, "corr") and hasattr(priors, "cov")):
+            raise TypeError("priors must be a GPPriors-like object or a dict")
+        if getattr(priors, "mean", None) is not None and getattr(getattr(priors, "mean"), "n_params", 0):
+            raise ValueError("mean-function priors are not supported: the designers assume a zero mean")
+        self.corr = list(priors.corr)
+        if len(self.corr) != d:
+            raise ValueError("bad number of correlation lengths in new GPPriors object")
+        self.cov = priors.cov
+        self.nugget = getattr(priors, "nugget", None)
+        self.d, self.fit_nugget = d, fit_nugget
+
+    @staticmethod
+    def _lp(dist, x):
+        return 0.0 if dist is None else float(dist.logp(x))
+
+    @staticmethod
+    def _dl(dist, x):
+        return 0.0 if dist is None else float(dist.dlogpdx(x))
+
+    def logp(self, theta_raw: np.ndarray) -> float:
+        d = self.d
+        total = 0.0
+        for k in range(d):
+            total += self._lp(self.corr[k], float(np.exp(-0.5 * theta_raw[k])))
+        total += self._lp(self.cov, float(np.exp(theta_raw[d])))
+        if self.fit_nugget:
+            total += self._lp(self.nugget, float(np.exp(theta_raw[d + 1])))
+        return total
+
+    def dlogp_draw(self, theta_raw: np.ndarray) -> np.ndarray:
+        d = self.d
+        out = np.zeros_like(theta_raw, dtype=float)
+        for k in range(d):
+            x = float(np.exp(-0.5 * theta_raw[k]))
+            out[k] = self._dl(self.corr[k], x) * (-0.5 * x)
+        x = float(np.exp(theta_raw[d]))
+        out[d] = self._dl(self.cov, x) * x
+        if self.fit_nugget:
+            x = float(np.exp(theta_raw[d + 1]))
+            out[d + 1] = self._dl(self.nugget, x) * x
+        return out
+
+    @staticmethod
+    def _draw(dist, to_raw) -> float:
+        if _is_flat(dist):
+            return float(5.0 * (np.random.rand() - 0.5))
+        return float(to_raw(dist.sample_x()))
+
+    def sample(self) -> np.ndarray:
+        pt = [self._draw(c, lambda x: -2.0 * np.log(x)) for c in self.corr]
+        pt.append(self._draw(self.cov, np.log))
+        if self.fit_nugget:
+            pt.append(self._draw(self.nugget, np.log))
+        return np.array(pt, dtype=float)
+
+
+def make_priors(priors, X: np.ndarray, fit_nugget: bool = False):
+    """``priors=None``: mogp's data-driven defaults (``MapPriors``); otherwise the user's (``CustomMapPriors``)."""
+    if priors is None:
+        return MapPriors(X, fit_nugget=fit_nugget)
+    return CustomMapPriors(priors, np.asarray(X).shape[1], fit_nugget=fit_nugget)
+
+
 class MapPriors:
     """Priors on (corr lengths..., process variance[, nugget]) for one training set."""
 

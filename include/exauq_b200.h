@@ -139,6 +139,20 @@ int exq_gp_destroy(exq_gp_t gp);
 int exq_gp_fit(exq_gp_t gp, const double* corr_raw, double cov, double nugget, int nugget_mode,
                double* nugget_used, double* logdet, double* quad);
 
+/* nugget = "pivot" (mogp GaussianProcess.fit -> linalg.pivot_cholesky -> LAPACK dpstrf; the option is passed through
+ * at exauq/core/emulators.py:129-137 and exercised by tests/unit/test_emulators.py:35, 683, 706).
+ * exq_gp_pivot_order: pivoted Cholesky (LAPACK's unblocked lower variant dpstf2: first arg max of the running
+ * Schur diagonal, stop at n * 2^-53 * max diag) of the nugget-free covariance of the handle's data; returns the
+ * 0-based pivot order piv[N] and the numerical rank.  The handle is left unfitted.
+ * exq_gp_fit_pivoted: the handle's data are ALREADY in pivot order (the host re-creates the handle with X[piv],
+ * y[piv], so that every downstream quantity keeps its triangular structure); factors the leading `rank` columns
+ * without interchanges, replaces the diagonal of the remaining rows by mogp's decreasing sequence
+ * L[rank-1][rank-1] / ((rank+1)...(i+1)), forms Linv and alpha as exq_gp_fit does.  The variance of predictions carries
+ * no nugget in this mode (mogp predict).  rank == N and a well-conditioned matrix: exq_gp_fit with nugget 0 on the
+ * permuted handle gives the same factor through the fast recursion. */
+int exq_gp_pivot_order(exq_gp_t gp, const double* corr_raw, double cov, int* piv, int* rank);
+int exq_gp_fit_pivoted(exq_gp_t gp, const double* corr_raw, double cov, int rank, double* logdet, double* quad);
+
 /* Predictive mean and variance at M points Xc[M][d] (host):
  * mean = k^T alpha, var = max(cov + nugget - k^T K^-1 k, 0).
  * Replaces mogp GaussianProcess.predict as called by MogpEmulator.predict,

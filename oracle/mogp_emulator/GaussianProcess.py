@@ -61,6 +61,36 @@ def jit_cholesky(A, maxtries=5):
     raise linalg.LinAlgError("not positive definite, even with jitter.")
 
 
+def pivot_cholesky(A):
+    """Pivoted Cholesky of a possibly singular covariance matrix (mogp-emulator 0.7.2, linalg/cholesky.py,
+    reached by ``GaussianProcess.fit`` when ``nugget == "pivot"``; option passed through at
+    exauq/core/emulators.py:129-137).  LAPACK ``dpstrf`` (lower, default tolerance n * eps * max diag) interchanges
+    rows / columns so that the diagonal of the factor decreases and stops at the numerical rank; the diagonal
+    entries of the skipped rows are then replaced by a decreasing sequence
+    ``L[rank-1, rank-1] / ((rank+1) (rank+2) ... (i+1))`` so that ``2 sum log diag L`` stays defined.  Returns
+    (L, P) with P the 0-based pivot order: ``A[P][:, P] = L L^T`` on the leading ``rank`` block.
+    NOTE: below the rank, what ``dpstrf`` leaves in the trailing block depends on LAPACK's block size, so values for
+    numerically rank-deficient matrices are not reproducible between LAPACK builds (parity there is unpinned)."""
+    A = np.ascontiguousarray(A)
+    assert A.ndim == 2 and A.shape[0] == A.shape[1], "A must be a square matrix"
+    L, P, rank, info = lapack.dpstrf(A, lower=1)
+    L = np.tril(L)
+    if info < 0:
+        raise linalg.LinAlgError("Illegal value in covariance matrix")
+    n = A.shape[0]
+    idx = np.arange(rank, n)
+    divs = np.cumprod(np.arange(rank + 1, n + 1, dtype=np.float64))
+    L[idx, idx] = L[rank - 1, rank - 1] / divs
+    return L, P - 1
+
+
+def _pivot_transpose(P):
+    "inverse of the permutation P"
+    out = np.empty(len(P), dtype=np.int32)
+    out[np.asarray(P)] = np.arange(len(P), dtype=np.int32)
+    return out
+
+
 class GaussianProcessBase(object):
     pass
 
@@ -162,8 +192,15 @@ class GaussianProcess(GaussianProcessBase):
     def priors(self, newpriors):
         if newpriors is None:
             newpriors = GPPriors.default_priors(self._inputs, self.n_corr, self._nugget_type)
+        if isinstance(newpriors, dict):
+            kw = dict(newpriors)
+            kw.setdefault("n_corr", self.n_corr)
+            kw["nugget_type"] = self._nugget_type
+            newpriors = GPPriors(**kw)
         if not isinstance(newpriors, GPPriors):
             raise TypeError("priors must be a GPPriors object in the oracle")
+        if self.n > 0 and newpriors.n_corr != self.n_corr:      # (an empty GP, as MogpEmulator first builds, has no shape yet)
+            raise ValueError("bad number of correlation lengths in new GPPriors object")
         self._priors = newpriors
 
     @property
@@ -200,23 +237,26 @@ class GaussianProcess(GaussianProcessBase):
             self.L, jitter = jit_cholesky(self.K)
             self._theta.nugget = jitter
         elif self._nugget_type == "pivot":
-            # pivoted Cholesky is outside the restated surface;
-            # approximated by the adaptive path.
-            self.L, jitter = jit_cholesky(self.K)
-            self._theta.nugget = jitter
+            self.L, self.P = pivot_cholesky(self.K)
         else:
             Kn = self.K + np.eye(self.n) * self._theta.nugget
             L, info = lapack.dpotrf(np.ascontiguousarray(Kn), lower=1)
             if info != 0:
                 raise linalg.LinAlgError("covariance matrix is not positive definite")
             self.L = L
-        self.Kinv_t = linalg.cho_solve((self.L, True), self._targets)
+        self.Kinv_t = self._kinv_solve(self._targets)
         self.current_logpost = 0.5 * (
             2.0 * np.sum(np.log(np.diag(self.L)))
             + np.dot(self._targets, self.Kinv_t)
             + self.n * np.log(2.0 * np.pi)
         )
         self.current_logpost -= self._priors.logp(self._theta)
+
+    def _kinv_solve(self, b):
+        "K^-1 b through the factor of the last fit (ChoInv / ChoInvPivot.solve in mogp)"
+        if self._nugget_type == "pivot":
+            return linalg.cho_solve((self.L, True), b[self.P])[_pivot_transpose(self.P)]
+        return linalg.cho_solve((self.L, True), b)
 
     def fit(self, theta):
         self.theta = theta
@@ -240,13 +280,13 @@ class GaussianProcess(GaussianProcessBase):
             self._inputs, self._inputs, self._theta.corr_raw)
         alpha = self.Kinv_t
         for d in range(self.D):
-            trace = np.trace(linalg.cho_solve((self.L, True), dKdtheta[d]))
+            trace = np.trace(self._kinv_solve(dKdtheta[d]))
             partials[d] = -0.5 * (np.dot(alpha, np.dot(dKdtheta[d], alpha)) - trace)
-        trace = np.trace(linalg.cho_solve((self.L, True), self.K))
+        trace = np.trace(self._kinv_solve(self.K))
         partials[self.D] = -0.5 * (np.dot(alpha, np.dot(self.K, alpha)) - trace)
         if self._nugget_type == "fit":
             nugget = self._theta.nugget
-            Kinv = linalg.cho_solve((self.L, True), np.eye(self.n))
+            Kinv = self._kinv_solve(np.eye(self.n))
             partials[-1] = 0.5 * nugget * (np.trace(Kinv) - np.dot(alpha, alpha))
         partials -= self._priors.dlogpdtheta(self._theta)
         return partials
@@ -268,7 +308,7 @@ class GaussianProcess(GaussianProcessBase):
             if include_nugget and self._nugget_type != "pivot":
                 sigma_2 = sigma_2 + self._theta.nugget
             var = np.maximum(
-                sigma_2 - np.sum(Ktest * linalg.cho_solve((self.L, True), Ktest), axis=0), 0.0)
+                sigma_2 - np.sum(Ktest * self._kinv_solve(Ktest), axis=0), 0.0)
         return PredictResult(mean=mu, unc=var, deriv=None)
 
     def __call__(self, testing):

@@ -1,5 +1,8 @@
-"""Hyperparameter priors of mogp-emulator 0.7.2 (restated; the subset reached when
-``priors=None``, which is all ``MogpEmulator`` ever uses -- exauq/core/emulators.py:129-137).
+"""Hyperparameter priors of mogp-emulator 0.7.2 (restated): the defaults reached when ``priors=None`` and the
+user-supplied case (``priors=`` is passed through by ``MogpEmulator``, exauq/core/emulators.py:129-137):
+``GPPriors`` of ``InvGammaPrior`` / ``GammaPrior`` / ``LogNormalPrior`` / ``WeakPrior`` entries or a dict of its
+keyword arguments.  The densities are the textbook ones in mogp's (shape, scale) parametrisation; without the
+wheel their agreement with mogp is unpinned beyond that.
 
 Used by the reference at exauq/utilities/mogp_fitting.py:316 (``gp.priors.sample()``) and
 inside ``logposterior``/``logpost_deriv`` (:318-324).
@@ -143,11 +146,45 @@ class InvGammaPrior(PriorDist):
         return float(scipy.stats.invgamma.rvs(self.shape, scale=self.scale))
 
 
+class GammaPrior(InvGammaPrior):
+    def logp(self, x):
+        return float(
+            -self.shape * np.log(self.scale) - gammaln(self.shape) + (self.shape - 1.0) * np.log(x) - x / self.scale
+        )
+
+    def dlogpdx(self, x):
+        return float((self.shape - 1.0) / x - 1.0 / self.scale)
+
+    def cdf(self, x):
+        return scipy.stats.gamma.cdf(x, self.shape, scale=self.scale)
+
+    def sample_x(self):
+        return float(scipy.stats.gamma.rvs(self.shape, scale=self.scale))
+
+
+class LogNormalPrior(InvGammaPrior):
+    def logp(self, x):
+        return float(
+            -0.5 * (np.log(x / self.scale) / self.shape) ** 2 - 0.5 * np.log(2.0 * np.pi) - np.log(x) - np.log(self.shape)
+        )
+
+    def dlogpdx(self, x):
+        return float(-np.log(x / self.scale) / self.shape**2 / x - 1.0 / x)
+
+    def cdf(self, x):
+        return scipy.stats.lognorm.cdf(x, self.shape, scale=self.scale)
+
+    def sample_x(self):
+        return float(scipy.stats.lognorm.rvs(self.shape, scale=self.scale))
+
+
 class GPPriors(object):
-    def __init__(self, corr=None, cov=None, nugget=None, n_corr=None, nugget_type="fit"):
+    def __init__(self, mean=None, corr=None, cov=None, nugget=None, n_corr=None, nugget_type="fit"):
+        assert mean is None, "only the zero mean function is restated in the oracle"
         if corr is None:
             assert n_corr is not None
             corr = [WeakPrior() for _ in range(n_corr)]
+        corr = [WeakPrior() if c is None else c for c in corr]
         self.corr = list(corr)
         self.cov = cov if cov is not None else WeakPrior()
         self.nugget_type = nugget_type
