@@ -40,6 +40,7 @@ SIGNATURES = {
     "exq_set_fused": (C.c_int, [C.c_int, C.c_int]),
     "exq_fused_info": (C.c_int, [_ip, _ip, _ip]),
     "exq_set_pei_fused": (C.c_int, [C.c_int]),
+    "exq_set_grad_fused": (C.c_int, [C.c_int]),
     "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
     "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "exq_timer_start": (C.c_int, []),
@@ -480,6 +481,12 @@ def set_pei_fused(on: bool = True) -> None:
     """Fused prediction / PEI pipeline (no FP64 covariance chunk) on or off (round-1 three-pass pipeline)."""
     init()
     check(load().exq_set_pei_fused(1 if on else 0), "exq_set_pei_fused")
+
+
+def set_grad_fused(on: bool = True) -> None:
+    """Gradient contraction in the epilogue of the int8 LAUUM kernel (on) or as a separate kernel over a stored K^-1."""
+    init()
+    check(load().exq_set_grad_fused(1 if on else 0), "exq_set_grad_fused")
 
 
 def fused_info() -> dict:

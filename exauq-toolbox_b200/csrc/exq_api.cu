@@ -58,6 +58,7 @@ struct Ctx {
     size_t kct_elems = 0, p_elems = 0;
     double* PMR = nullptr;           // [2][Np/64][chunk] partial means / repulsion products of the fused PEI pipeline
     size_t pmr_elems = 0;
+    int grad_fused = 1;              // EXQ_GRAD_FUSED=0: K^-1 stored by LAUUM and contracted by a separate gradient kernel
     int pei_fused = 1;               // EXQ_PEI_FUSED=0: round-1 pipeline (FP64 chunk -> slicer -> per-candidate epilogue)
     // int8 tcgen05 variance path (ozaki_i8.cuh): digits per operand (EXQ_OZAKI_SLICES = 0 keeps the FP64 DMMA
     // GEMM, 5..7 selects the number of base-256 digits; 6 = 48 bits is ~2e-12 absolute on the variance)
@@ -463,7 +464,7 @@ bool factor_uses_int8(const Sys& s) {
 
 template <int S>
 int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-              int cmode, double fl, bool reuse_a) {
+              int cmode, double fl, bool reuse_a, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
     int rc;
     const int64_t ld = s.Np, sq = s.sq();
     int* expA = s.oz_exp;
@@ -481,12 +482,21 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.expA = expA; a.expB = expB; a.C = C; a.ldc = ld; a.strideC = sq;
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
+    if (ga) a.g = *ga;
     a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
     // int8 operations issued: every non-skipped (128 x 64) tile runs S(S+1)/2 digit products over its k range --
     // counted by the same tile walk the kernel does (round 1 counted LAUUM twice: 2/3 instead of 1/3 of the cube)
     m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, oz::gemm_issued_ops(M, N, K, s.B, krange, lower_only, S));
-    rc = oz::launch_gemm<S>(planesA, planesB, a, g.sm_count, g.stream);
+    if (ga) {
+        a.g.slots = std::min(g.sm_count, (M / oz::BLK_C) * (N / oz::BLK_R) * s.B) * oz::EPI_WARPS;
+        cudaMemsetAsync(a.g.partial, 0, (size_t)s.B * a.g.slots * (oz::GRAD_D + 2) * sizeof(double), g.stream);
+    }
+    rc = oz::launch_gemm<S>(planesA, planesB, a, g.sm_count, g.stream, grad_kernel_id);
     prof_end(m);
+    if (!rc && ga) {
+        oz::grad_reduce_slots_kernel<<<s.B, 32, 0, g.stream>>>(a.g.partial, a.g.slots, a.g.d, s.grad);
+        g.launches++;
+    }
     if (rc)
         return fail(EXQ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the int8 GEMM: CUresult " + std::to_string(rc) + " M=" +
                                       std::to_string(M) + " N=" + std::to_string(N) + " K=" + std::to_string(K) + " B=" +
@@ -496,7 +506,7 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
 }
 
 int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-            int cmode, bool reuse_a = false, int digits = 0) {
+            int cmode, bool reuse_a = false, int digits = 0, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
     double fl = 2.0 * M * (double)N * K * s.B;
     if (krange != KR_FULL) fl *= 0.5;
     if (lower_only && krange == KR_FULL) fl *= 0.5;
@@ -505,8 +515,8 @@ int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int 
     if ((digits != 6 && digits != 7) || !oz_planes_fit(s, digits, M, N, K, same))
         return fail(EXQ_ERR_STATE, "int8 GEMM: " + std::to_string(digits) + " digits of a " + std::to_string(M) + " x " +
                                        std::to_string(K) + " operand do not fit the digit-plane workspace");
-    if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
-    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a);
+    if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id);
+    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id);
 }
 
 // potrf + trtri of the diagonal block [r0, r0+n) of every system in s by ONE launch of fused_factor_kernel
@@ -659,7 +669,9 @@ int refine_alpha(Sys& s, const double* X, int64_t strideX, const double* y, int6
 
 // K^-1 (lower tiles) into s.W; digits: base-256 digits of the int8 product (0: the configured LAUUM digits);
 // have_dinv: s.dinv holds the column sums of squares of Linv (solve_vectors ran on these systems)
-int lauum(Sys& s, int digits = 0, bool have_dinv = false) {
+// ga != nullptr: K^-1 is not stored -- the int8 kernel's epilogue contracts it with dK/dtheta (C_GRAD) and s.grad
+// receives the gradient; only when lauum_fuses_grad() said so
+int lauum(Sys& s, int digits = 0, bool have_dinv = false, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
     GemmArgs a{};
     a.lda = a.ldb = a.ldc = s.Np;
     a.strideA = a.strideB = a.strideC = s.sq();
@@ -667,8 +679,10 @@ int lauum(Sys& s, int digits = 0, bool have_dinv = false) {
     a.krange = KR_GE_I; a.lower_only = 1; a.cmode = C_STORE;
     if (oz_gemm_wanted(s, s.Np, s.Np, s.Np, true))
         return oz_gemm(s, {s.Linv, 1, oz::MASK_GE, have_dinv ? s.dinv : nullptr}, {s.Linv, 1, oz::MASK_GE}, true, s.W, s.Np, s.Np,
-                       s.Np, KR_GE_I, 1, C_STORE,
-                       false, digits ? std::min(digits, g.oz_factor_slices) : std::min(g.oz_lauum_slices, g.oz_factor_slices));
+                       s.Np, KR_GE_I, 1, ga ? C_GRAD : C_STORE,
+                       false, digits ? std::min(digits, g.oz_factor_slices) : std::min(g.oz_lauum_slices, g.oz_factor_slices),
+                       ga, grad_kernel_id);
+    if (ga) return fail(EXQ_ERR_STATE, "lauum: fused gradient needs the int8 kernel");
     return launch_gemm<LAYOUT_MN, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR);
 }
 
@@ -970,6 +984,14 @@ int enqueue_factor(exq_gp_t gp, Sys& s, const double* theta_host) {
 int enqueue_grad(exq_gp_t gp, Sys& s, int dmax, int lauum_digits) {
     const int N = (int)gp->N, d = gp->d, Np = gp->Np, nt = Np / 128, B = s.B;
     int rc;
+    // LAUUM on the int8 kernel, stationary kernel, d <= 8: the gradient contraction rides in the GEMM's epilogue
+    if (g.grad_fused && d <= oz::GRAD_D && gp->kernel_id != EXQ_KERNEL_PRODMAT52 && g.fast_corr &&
+        oz_gemm_wanted(s, Np, Np, Np, true) &&
+        (size_t)g.sm_count * oz::EPI_WARPS * (oz::GRAD_D + 2) <= (size_t)nt * nt * (64 + 2)) {
+        oz::GradArgs ga{};
+        ga.X = gp->X; ga.theta = s.theta; ga.alpha = s.alpha; ga.ldv = Np; ga.n_valid = N; ga.d = d; ga.partial = s.gpartial;
+        return lauum(s, lauum_digits, /*have_dinv=*/true, &ga, gp->kernel_id);
+    }
     if ((rc = lauum(s, lauum_digits, /*have_dinv=*/true))) return rc;
     size_t smem = ((size_t)128 * d + (size_t)d * GRAD_XT_LD + d + 2 + 256 + 8 * (dmax + 2)) * sizeof(double);
     dim3 grid(nt, nt, B);
@@ -1085,6 +1107,7 @@ int exq_init(int device) {
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
     if (const char* e = getenv("EXQ_PEI_FUSED")) g.pei_fused = atoi(e) != 0;
+    if (const char* e = getenv("EXQ_GRAD_FUSED")) g.grad_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_FUSE_N")) { const int v = atoi(e); g.fuse_n = (v >= 256 && v <= 1024) ? (v / 128) * 128 : 0; }
     if (const char* e = getenv("EXQ_FUSE_G")) { const int v = atoi(e); g.fuse_g = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : 0; }
     if (const char* e = getenv("EXQ_REFINE_STEPS")) g.refine_steps = std::max(0, std::min(4, atoi(e)));
@@ -1167,6 +1190,11 @@ int exq_set_fused(int max_rows, int cluster_ctas) {
 int exq_set_pei_fused(int on) {
     REQUIRE_READY();
     g.pei_fused = on != 0;
+    return EXQ_OK;
+}
+int exq_set_grad_fused(int on) {
+    REQUIRE_READY();
+    g.grad_fused = on != 0;
     return EXQ_OK;
 }
 int exq_set_refine_steps(int steps) {

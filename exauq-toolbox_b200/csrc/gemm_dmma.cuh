@@ -19,7 +19,7 @@ namespace exq {
 
 enum : int { LAYOUT_K = 0, LAYOUT_MN = 1 };          // which index is contiguous in memory
 enum : int { KR_FULL = 0, KR_LE_J = 1, KR_GE_J = 2, KR_LE_I = 3, KR_GE_I = 4 };
-enum : int { C_STORE = 0, C_SUB = 1, C_NEG = 2, C_COLSUMSQ = 3 };
+enum : int { C_STORE = 0, C_SUB = 1, C_NEG = 2, C_COLSUMSQ = 3, C_GRAD = 4 /* int8 kernel only: see ozaki_gemm.cuh */ };
 
 struct GemmArgs {
     const double* A;   // LAYOUT_K: A[i*lda + k]    LAYOUT_MN: A[k*lda + i]

@@ -165,7 +165,30 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restric
     }
 }
 
+// cmode == C_GRAD (LAUUM only, kernels instantiated with GK >= 0): the tile of K^-1 = Linv^T Linv is not stored; the
+// epilogue contracts it with dK/dtheta on the spot --
+//     grad_k = 1/2 sum_ij (K^-1 - alpha alpha^T)_ij dK_ij/d raw_k     (mogp logpost_deriv, exauq/utilities/mogp_fitting.py:318-324)
+// -- while the tensor pipe runs the next tile: the ~65 FP64 operations per entry that used to be a kernel of their own
+// (grad_fast_kernel: 1.45 ms per round of 15 systems, FP64 pipe 35 % active at 8 warps per SM) ride on the idle
+// FP64 pipe under the int8 MMAs, and K^-1 (1 GB per round) never goes to HBM.  Same pair arithmetic as
+// grad_fast_kernel; per (system, CTA, epilogue warp) partial sums in fixed order, reduced by grad_reduce_slots_kernel.
+constexpr int GRAD_D = 8;       // input dimensions the fused epilogue holds in registers (d <= 8)
+#ifndef EXQ_GRAD_ILP
+#define EXQ_GRAD_ILP 4
+#endif
+constexpr int GRAD_ILP = EXQ_GRAD_ILP;   // (i, j) pairs in flight per epilogue thread
+struct GradArgs {
+    const double* X;        // [Np][d] training inputs, zero padded (shared by all systems)
+    const double* theta;    // [B][d + 2]: exp(raw_k), sigma2, nugget
+    const double* alpha;    // [B][ldv]
+    int64_t ldv;
+    int n_valid, d;
+    double* partial;        // [B][slots][GRAD_D + 2], zeroed by the host; slot = CTA * EPI_WARPS + epilogue warp
+    int slots;
+};
+
 struct GArgs {
+    GradArgs g;
     const int* expA;      // [B][M]
     const int* expB;      // [B][N]
     double* C;
@@ -231,7 +254,10 @@ __device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& 
     return !tile_skipped(a.lower_only, I, J);
 }
 
-template <int S>
+// GK: -1 plain GEMM; EXQ_KERNEL_MATERN52 / EXQ_KERNEL_SQEXP: cmode C_GRAD is available (fused gradient contraction)
+// (320 threads are budgeted as 384 by the register allocator: 168 registers per thread is the hardware limit here --
+// a launch with 192 fails with "too many resources" -- so the gradient epilogue lives with ~200 bytes of spills)
+template <int S, int GK = -1>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GArgs a) {
     using C = Cfg<S>;
@@ -244,6 +270,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+    // fused gradient epilogue: the tile's 64 columns (pre-scaled coordinates, alpha), shared by the epilogue warps
+    __shared__ __align__(16) double gx_s[(GK >= 0 ? GRAD_D : 2) * (GK >= 0 ? BLK_R : 1)];
+    __shared__ double ga_s[GK >= 0 ? BLK_R : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
@@ -331,6 +361,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         uint32_t acc_ph = 0;
         constexpr double LO_W = 1.0 / (double)(1ull << (W * (S - 4)));
+        // fused gradient contraction: running sums of this thread for the system it is working on
+        constexpr int GD = GK >= 0 ? GRAD_D : 2;
+        double gacc[GD + 2];
+        int g_sys = -1;
+        const bool do_grad = GK >= 0 && a.cmode == C_GRAD;
+        auto grad_flush = [&]() {
+            if (g_sys < 0) return;
+            double* out = a.g.partial + ((int64_t)g_sys * a.g.slots + (int64_t)blockIdx.x * EPI_WARPS + (warp - 2)) * (GD + 2);
+#pragma unroll
+            for (int k = 0; k < GD + 2; k++) {
+                const double v = warp_sum(gacc[k]);
+                if (lane == 0) out[k] = v;
+                gacc[k] = 0.0;
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < GD + 2; k++) gacc[k] = 0.0;
         for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
             int b, I, J;
             if (!decode_gemm_item(a, i, b, I, J)) continue;
@@ -368,6 +415,97 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             // phase 2: scale and write the FP64 tile row
 #pragma unroll
             for (int c = 0; c < 32; c++) z[c] = z[c] * row_scale * pow2d(__ldg(eb + c));
+            if (GK >= 0 && do_grad) {
+                if (b != g_sys) {                       // items are ordered by system: one flush per (CTA, system)
+                    grad_flush();
+                    g_sys = b;
+                }
+                const double* th = a.g.theta + (int64_t)b * (a.g.d + 2);
+                const double g_sigma2 = __ldg(th + a.g.d), g_nugget = __ldg(th + a.g.d + 1);
+                const double* al = a.g.alpha + (int64_t)b * a.g.ldv;
+                // the tile's 64 columns: coordinates pre-scaled by sqrt(w_k) and alpha, staged once for the eight
+                // epilogue warps (they all work on the same item); barrier 1 = the 256 epilogue threads
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // the previous tile's readers are done
+                {
+                    const int et = threadIdx.x - 64;
+                    for (int e = et; e < GD * BLK_R; e += EPI_WARPS * 32) {
+                        const int c = e / GD, k = e - c * GD;           // [column][k]: two coordinates per 16-byte read
+                        gx_s[e] = (k < a.g.d) ? sqrt(__ldg(th + k)) * __ldg(a.g.X + (int64_t)(J * BLK_R + c) * a.g.d + k) : 0.0;
+                    }
+                    if (et < BLK_R) ga_s[et] = __ldg(al + J * BLK_R + et);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int gi = row;
+                const bool row_ok = gi < a.g.n_valid;
+                const double ai = __ldg(al + gi);
+                double xi[GD];
+#pragma unroll
+                for (int k = 0; k < GD; k++)
+                    xi[k] = (k < a.g.d) ? sqrt(__ldg(th + k)) * __ldg(a.g.X + (int64_t)gi * a.g.d + k) : 0.0;
+                const int gj0 = J * BLK_R + half * 32;
+                const double2* gxh = reinterpret_cast<const double2*>(gx_s + half * 32 * GD);
+                const double* gah = ga_s + half * 32;
+#ifdef EXQ_GRAD_SKIP_MATH
+                if (false)
+#endif
+#pragma unroll 1
+                for (int c0 = 0; c0 < 32; c0 += GRAD_ILP) {
+                    // ONE copy of the pair arithmetic with GRAD_ILP pairs in flight (the FP64 chains of exp / sqrt need
+                    // that many independent instructions per warp: there are only two epilogue warps per scheduler).
+                    // The loop always works on z[0 .. GRAD_ILP) and rotates the array down at the end of the iteration,
+                    // so z[] keeps constant indices (registers).  The coordinate differences are formed twice (for r^2
+                    // and for the contraction) instead of being kept, and sqrt(w_k) is folded into the coordinates:
+                    // d r^2 / d raw_k is then just (dx'_k)^2.  r2[] holds r^2, then f_ij = (K^-1 - a a^T)_ij sigma2 dcorr/dr^2.
+                    double r2[GRAD_ILP];
+#pragma unroll
+                    for (int u = 0; u < GRAD_ILP; u++) r2[u] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < GD; k += 2) {
+#pragma unroll
+                        for (int u = 0; u < GRAD_ILP; u++) {
+                            const double2 xj = gxh[(c0 + u) * (GD / 2) + (k >> 1)];
+                            const double d0 = xi[k] - xj.x, d1 = xi[k + 1] - xj.y;
+                            r2[u] = fma(d0, d0, r2[u]);
+                            r2[u] = fma(d1, d1, r2[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < GRAD_ILP; u++) {
+                        const int gj = gj0 + c0 + u;
+                        const double wij = z[u] - ai * gah[c0 + u];
+                        const double wv = (row_ok && gj < gi) ? wij * g_sigma2 : 0.0;   // strictly lower triangle, no padding
+                        if (row_ok && gj == gi) {                           // dK_ii / d ln sigma2 = sigma2, / d ln nugget = nugget
+                            gacc[GD] = fma(0.5 * wij, g_sigma2, gacc[GD]);
+                            gacc[GD + 1] = fma(0.5 * wij, g_nugget, gacc[GD + 1]);
+                        }
+                        double cv, dv;
+                        if (GK == EXQ_KERNEL_MATERN52) {
+                            const double s5 = sqrt_nonneg(5.0 * r2[u]), e = exp_nonpos(-s5);
+                            cv = (1.0 + s5 + (5.0 / 3.0) * r2[u]) * e;
+                            dv = (-5.0 / 6.0) * (1.0 + s5) * e;
+                        } else {
+                            cv = exp_nonpos(-0.5 * r2[u]);
+                            dv = -0.5 * cv;
+                        }
+                        gacc[GD] = fma(wv, cv, gacc[GD]);
+                        r2[u] = wv * dv;
+                    }
+#pragma unroll
+                    for (int k = 0; k < GD; k += 2) {
+#pragma unroll
+                        for (int u = 0; u < GRAD_ILP; u++) {
+                            const double2 xj = gxh[(c0 + u) * (GD / 2) + (k >> 1)];
+                            const double d0 = xi[k] - xj.x, d1 = xi[k + 1] - xj.y;
+                            gacc[k] = fma(r2[u] * d0, d0, gacc[k]);
+                            gacc[k + 1] = fma(r2[u] * d1, d1, gacc[k + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32 - GRAD_ILP; c++) z[c] = z[c + GRAD_ILP];
+                }
+                acc_ph ^= 1u;
+                continue;
+            }
             double2* cp = reinterpret_cast<double2*>(crow);
             if (a.cmode == C_STORE) {
 #pragma unroll
@@ -384,6 +522,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             acc_ph ^= 1u;
         }
+        if (GK >= 0 && do_grad) grad_flush();
     }
 
     tc_fence_before();
@@ -394,9 +533,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 }
 
+// sum the per-(CTA, epilogue warp) partials of the fused gradient epilogue in fixed order -> grad[b][0..d-1], [d], [d+1]
+__global__ void grad_reduce_slots_kernel(const double* __restrict__ partial, int slots, int d, double* __restrict__ grad) {
+    const int b = blockIdx.x, k = threadIdx.x;
+    if (k >= d + 2) return;
+    const int src = (k < d) ? k : (GRAD_D + (k - d));
+    double s = 0.0;
+    for (int t = 0; t < slots; t++) s += partial[((int64_t)b * slots + t) * (GRAD_D + 2) + src];
+    grad[(int64_t)b * (d + 2) + k] = s;
+}
+
 template <int S>
 inline cudaError_t set_gemm_attrs() {
-    return cudaFuncSetAttribute(gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<S, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    return e;
 }
 
 // One operand of an int8 GEMM: exponents + digit planes for a batch of B matrices (rows x K each)
@@ -423,15 +577,24 @@ inline void slice_operand(const double* src, int64_t ld, int64_t stride_sys, int
 }
 
 // C (op)= A B^T from digit planes: planesA [S][B*M][K], planesB [S][B*N][K]
+// grad_kernel_id >= 0 with a.cmode == C_GRAD: the instantiation that carries the fused gradient epilogue
 template <int S>
-inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs& a, int sm_count, cudaStream_t stream) {
+inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs& a, int sm_count, cudaStream_t stream,
+                       int grad_kernel_id = -1) {
     CUtensorMap ma, mb;
     int rc;
     if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C))) return rc;
     if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R))) return rc;
     const int items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
     const int grid = items < sm_count ? items : sm_count;
-    gemm_kernel<S><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+    if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_MATERN52)
+        gemm_kernel<S, EXQ_KERNEL_MATERN52><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+    else if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_SQEXP)
+        gemm_kernel<S, EXQ_KERNEL_SQEXP><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+    else if (a.cmode == C_GRAD)
+        return -1;
+    else
+        gemm_kernel<S, -1><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
     return 0;
 }
 

@@ -88,6 +88,11 @@ int exq_set_fused(int max_rows, int cluster_ctas);
  * slicer, per-candidate epilogue).  EXQ_PEI_FUSED.  Same quantities either way (mogp GaussianProcess.predict,
  * exauq/core/emulators.py:649; PEICalculator.compute, exauq/core/designers.py:522-706). */
 int exq_set_pei_fused(int on);
+/* Gradient of the log-posterior (mogp logpost_deriv, exauq/utilities/mogp_fitting.py:318-324).  on (default): when
+ * K^-1 = Linv^T Linv runs on the int8 kernel (stationary kernels, d <= 8) its epilogue contracts every tile with
+ * dK/dtheta while the tensor pipe works on the next one -- K^-1 is never stored and there is no gradient kernel.
+ * off: LAUUM stores K^-1 and grad_fast_kernel contracts it (round 2's first half).  EXQ_GRAD_FUSED. */
+int exq_set_grad_fused(int on);
 /* current max_rows and how many clusters of 8 / 16 CTAs of that kernel the device co-schedules */
 int exq_fused_info(int* max_rows, int* clusters8, int* clusters16);
 /* kappa of the last exq_gp_fit of this handle and whether the guard sent that fit to FP64 DMMA */

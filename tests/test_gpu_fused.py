@@ -126,3 +126,36 @@ def test_fused_pei_pipeline_equals_three_pass_pipeline_and_oracle(exq, orc, kern
         assert out[True][3].tolist() == oi.tolist()
         assert np.allclose(out[True][4], ov, rtol=1e-6)
     dev.close()
+
+
+@pytest.mark.parametrize("kernel,N,d,R,fit_nugget", [("Matern52", 4096, 8, 15, False), ("SquaredExponential", 2300, 5, 6, False),
+                                                     ("Matern52", 2048, 3, 4, True)])
+def test_gradient_in_lauum_epilogue_equals_separate_kernel(exq, kernel, N, d, R, fit_nugget):
+    """The int8 LAUUM kernel's C_GRAD epilogue (csrc/ozaki_gemm.cuh: K^-1 tiles contracted with dK/dtheta on the spot,
+    never stored) against LAUUM + grad_fast_kernel on the same digits: the K^-1 entries are the same numbers, only the
+    order of the FP64 summation differs.  The oracle comparison of the default (fused) path is
+    tests/test_gpu_illcond.py / test_gpu_parity.py (mogp logpost_deriv, exauq/utilities/mogp_fitting.py:318-324)."""
+    lib = exq._lib
+    from oracle import gp_oracle as orc
+
+    X, y = orc.synthetic_problem(N, d)
+    rng = np.random.default_rng(N + d)
+    raw = np.full(d, -2 * np.log(0.45 if kernel == "Matern52" else 0.2))
+    cols = [raw + rng.uniform(-0.5, 0.5, (R, d)), np.log(1.7) + rng.uniform(-0.4, 0.4, (R, 1))]
+    if fit_nugget:
+        cols.append(np.log(1e-6) + rng.uniform(-1, 1, (R, 1)))
+    thetas = np.concatenate(cols, axis=1)
+    dev = exq.DeviceGP(X, y, kernel)
+    out = {}
+    for mode in (False, True):
+        lib.set_grad_fused(mode)
+        n0 = lib.launch_count()
+        out[mode] = dev.logpost_batch(thetas, 1e-8, fit_nugget=fit_nugget)
+        out[mode] += (lib.launch_count() - n0,)
+    lib.set_grad_fused(True)
+    assert np.all(out[True][2] == 0) and np.all(out[False][2] == 0)
+    assert np.array_equal(out[True][0], out[False][0])                      # values do not involve the gradient path
+    gmax = np.max(np.abs(out[False][1]), axis=1, keepdims=True)
+    assert np.all(np.abs(out[True][1] - out[False][1]) <= 1e-11 * gmax)
+    assert out[True][4] < out[False][4]                                     # one kernel less per evaluation round
+    dev.close()
