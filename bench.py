@@ -329,10 +329,10 @@ def run_b200(a):
     # nodes, vector kernels) are timed in one extra, untimed step below so that their event records do not perturb
     # the headline.
     big = ((1 << _lib.PROF_GEMM_PREDICT) | (1 << _lib.PROF_GEMM_FACTOR_I8) | (1 << _lib.PROF_SLICE)
-           | (1 << _lib.PROF_ASSEMBLE))
+           | (1 << _lib.PROF_ASSEMBLE) | (1 << _lib.PROF_LAUUM_GRAD))
     if not _lib.factor_slices():
         big |= 1 << _lib.PROF_GEMM_FACTOR
-    names = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_factor_i8", "slice", "fused"]
+    names = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_factor_i8", "slice", "fused", "lauum_grad"]
     _lib.prof_enable(big)
     _lib.prof_reset()
     sampler = ClockSampler(local)
@@ -436,7 +436,9 @@ def run_b200(a):
     vname = ("oz::colsumsq_kernel[variance Z=Linv*Kc^T on int8 tcgen05, %d base-256 digits]" % slices if slices
              else "gemm_dmma_kernel[variance Z=Linv*Kc^T]")
     fslices = _lib.factor_slices()
-    fname = "oz::gemm_kernel[potrf/trtri nodes with k >= 1024 and LAUUM on int8 tcgen05, %d base-256 digits]" % fslices
+    fused_grad = prof["lauum_grad"]["launches"] > 0
+    fname = ("oz::gemm_kernel[potrf/trtri nodes with k >= 1024%s on int8 tcgen05, %d base-256 digits]"
+             % ("" if fused_grad else " and LAUUM", fslices))
     kern = {vname: roof(prof["gemm_predict"]),
             "gemm_dmma_kernel[potrf/trtri/lauum tiles]": roof(prof["gemm_factor"]),
             fname: roof(prof["gemm_factor_i8"])}
@@ -511,6 +513,15 @@ def run_b200(a):
             "avg_launch_ms": pf["ms"] / pf["launches"], "bound": "latency (leaf pivot chain) / FP64 DMMA",
             "achieved": pf["flops"] / (pf["ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": pf["flops"] / (pf["ms"] * 1e-3) / 1e12 / fp64_peak}
+    pl = prof["lauum_grad"]
+    if pl["launches"]:
+        # the int8 LAUUM whose epilogue contracts K^-1 with dK/dtheta on the FP64 pipe: two kinds of work in one launch,
+        # so it is listed on its own (int8 rate of the product alone; the gradient's ~73 FP64 operations per entry ride on top)
+        other["oz::gemm_kernel<6, grad>[K^-1 = Linv^T Linv on int8 tcgen05 + gradient contraction in the epilogue]"] = {
+            "ms_per_step": pl["ms"] / a.steps, "launches_per_step": pl["launches"] / a.steps,
+            "avg_launch_ms": pl["ms"] / pl["launches"], "bound": "FP64 pair arithmetic of the epilogue (2 warps per scheduler) "
+            "over the int8 mainloop", "int8_tops_of_the_product": pl["bytes"] / (pl["ms"] * 1e-3) / 1e12,
+            "fp64_equivalent_tflops_of_the_product": pl["flops"] / (pl["ms"] * 1e-3) / 1e12}
     for name in ("leaf", "assemble", "slice", "stream"):
         p = prof[name]
         if p["launches"]:

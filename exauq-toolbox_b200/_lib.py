@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("EXQ_LIB", os.path.join(_HERE, "libexauq_b200.so"))  #
 EXQ_OK, EXQ_ERR_ARG, EXQ_ERR_CUDA, EXQ_ERR_STATE, EXQ_NOT_PD = 0, -1, -2, -3, 1
 KERNEL_IDS = {"Matern52": 0, "SquaredExponential": 1, "ProductMat52": 2}
 NUGGET_FIXED, NUGGET_ADAPTIVE, NUGGET_FIT = 0, 1, 2
-PROF_GEMM_PREDICT, PROF_GEMM_FACTOR, PROF_LEAF, PROF_ASSEMBLE, PROF_STREAM, PROF_GEMM_FACTOR_I8, PROF_SLICE, PROF_FUSED = range(8)
+(PROF_GEMM_PREDICT, PROF_GEMM_FACTOR, PROF_LEAF, PROF_ASSEMBLE, PROF_STREAM, PROF_GEMM_FACTOR_I8, PROF_SLICE, PROF_FUSED,
+ PROF_LAUUM_GRAD) = range(9)
 
 # every symbol include/exauq_b200.h declares: (name, restype, argtypes)
 _dp = C.POINTER(C.c_double)

@@ -486,7 +486,7 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
     // int8 operations issued: every non-skipped (128 x 64) tile runs S(S+1)/2 digit products over its k range --
     // counted by the same tile walk the kernel does (round 1 counted LAUUM twice: 2/3 instead of 1/3 of the cube)
-    m = prof_begin(EXQ_PROF_GEMM_FACTOR_I8, fl, oz::gemm_issued_ops(M, N, K, s.B, krange, lower_only, S));
+    m = prof_begin(ga ? EXQ_PROF_LAUUM_GRAD : EXQ_PROF_GEMM_FACTOR_I8, fl, oz::gemm_issued_ops(M, N, K, s.B, krange, lower_only, S));
     if (ga) {
         a.g.slots = std::min(g.sm_count, (M / oz::BLK_C) * (N / oz::BLK_R) * s.B) * oz::EPI_WARPS;
         cudaMemsetAsync(a.g.partial, 0, (size_t)s.B * a.g.slots * (oz::GRAD_D + 2) * sizeof(double), g.stream);
@@ -882,7 +882,7 @@ int predict_device(exq_gp_t gp, const double* Xc, int64_t M, int64_t Mpad, const
                 fl_attr = true;
             }
             ProfMark mf = prof_begin(EXQ_PROF_STREAM, (double)mc * n_rep * (3.0 * gp->d + 30.0), (double)mc * (2.0 * nM + f.nP) * 8.0);
-            fin_light_kernel<<<(unsigned)((mc + 127) / 128), 128, fsmem, g.stream>>>(f);
+            fin_light_kernel<<<(unsigned)((mc * FIN_LANES + 127) / 128), 128, fsmem, g.stream>>>(f);
             prof_end(mf);
             LAUNCH_CHECK("fin_light_kernel");
             continue;

@@ -116,7 +116,9 @@ int exq_timer_stop(double* ms);
 #define EXQ_PROF_GEMM_FACTOR_I8 5 /* large nodes of the recursion + LAUUM on the int8 tensor cores (flops: FP64-equivalent) */
 #define EXQ_PROF_SLICE 6          /* exponent + base-256 digit passes feeding the int8 kernels (bytes moved) */
 #define EXQ_PROF_FUSED 7          /* fused sub-tree kernel: potrf + trtri of diagonal blocks <= 512 rows in one launch */
-#define EXQ_PROF_NCLASS 8
+#define EXQ_PROF_LAUUM_GRAD 8     /* int8 LAUUM launches whose epilogue carries the gradient contraction (int8 ops issued in
+                                   * `bytes`, FP64-equivalent LAUUM flops in `flops`; the FP64 pair arithmetic rides on top) */
+#define EXQ_PROF_NCLASS 9
 int exq_prof_enable(int class_mask); /* bit i set: time launches of class i with event pairs */
 int exq_prof_reset(void);
 int exq_prof_get(int cls, double* total_ms, int64_t* launches, double* flops, double* bytes);

@@ -25,9 +25,8 @@ def algorithmic_bytes_per_round(N, B, s_factor=7, s_lauum=6, min_k=1024):
         launches += 4 * count
         h //= 2
         count *= 2
-    total += s_lauum * N * N / 2 + 8 * N * N / 2
-    launches += 1
-    return B * total, launches
+    lauum = s_lauum * N * N / 2 + 8 * N * N / 2
+    return B * total, launches, B * lauum
 
 
 def main():
@@ -39,9 +38,10 @@ def main():
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    launches = []
+    launches, lauum_launches = [], []
     for r in rows[2:]:
-        if "gemm_kernel" not in r[col["Kernel Name"]] or "dmma" in r[col["Kernel Name"]]:
+        name = r[col["Kernel Name"]]
+        if "gemm_kernel" not in name or "dmma" in name:
             continue
         rd = float(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
@@ -50,8 +50,10 @@ def main():
         t_ms = t * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[tu]
         tp = r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]] if \
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in col else ""
-        launches.append({"dram_read": rd, "dram_write": wr, "ms_under_ncu": t_ms, "tensor_pipe_active_pct": tp})
-    alg, n_expected = algorithmic_bytes_per_round(N, B)
+        # the node products run with 7 digits, K^-1 = Linv^T Linv (LAUUM) with 6: told apart by the template argument
+        (lauum_launches if "<6" in name else launches).append(
+            {"kernel": name.split("(")[0], "dram_read": rd, "dram_write": wr, "ms_under_ncu": t_ms, "tensor_pipe_active_pct": tp})
+    alg, n_expected, alg_lauum = algorithmic_bytes_per_round(N, B)
     n = len(launches)
     res = {
         "oz::gemm_kernel": {
@@ -59,10 +61,15 @@ def main():
             "algorithmic_bytes_per_launch": alg / n_expected,
             "captured_launches": n, "launches_per_round": n_expected,
             "source": f"{os.path.basename(rep)}: ncu --set full --clock-control none of tools/ncu_target.py (NCU_TARGET_R={B}, "
-                      f"N={N}); mean over the {n} captured launches of one evaluation round; algorithmic = digit planes "
-                      "read once + FP64 result tiles written (SYRK: read and written), tools/ncu_traffic.py",
+                      f"N={N}); mean over the {n} captured node-product launches (7 digits) of one evaluation round; "
+                      "algorithmic = digit planes read once + FP64 result tiles written (SYRK: read and written), "
+                      "tools/ncu_traffic.py",
             "launches": launches,
-        }
+        },
+        "oz::gemm_kernel<6> LAUUM (captured before the gradient moved into its epilogue: it still stored K^-1)": {
+            "dram_bytes_per_launch": sum(l["dram_read"] + l["dram_write"] for l in lauum_launches) / max(len(lauum_launches), 1),
+            "algorithmic_bytes_per_launch": alg_lauum, "launches": lauum_launches,
+        },
     }
     path = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     json.dump(res, open(path, "w"), indent=1)

@@ -28,7 +28,7 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 _lib.init(0)
 X, y = synthetic_problem(N, d)
 g = exq.DeviceGP(X, y, "Matern52")
-NAMES = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_i8", "slice", "fused"]
+NAMES = ["gemm_predict", "gemm_factor", "leaf", "assemble", "stream", "gemm_i8", "slice", "fused", "lauum_grad"]
 base = np.concatenate([np.full(d, -2 * np.log(0.5)), [np.log(1.7)]])
 rows = []
 for B in (1, 2, 3, 4, 8, 15, 30):
@@ -41,7 +41,7 @@ for B in (1, 2, 3, 4, 8, 15, 30):
     for _ in range(reps):
         g.logpost_batch(th, 0.0)
     ms = _lib.timer_stop() / reps
-    _lib.prof_enable(0xFF)
+    _lib.prof_enable(0x1FF)
     _lib.prof_reset()
     g.logpost_batch(th, 0.0)
     out = {"N": N, "d": d, "systems": B, "ms_per_round": round(ms, 3), "ms_per_system": round(ms / B, 3)}
