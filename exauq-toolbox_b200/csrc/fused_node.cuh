@@ -22,6 +22,19 @@
 
 namespace exq {
 
+#ifdef EXQ_FUSED_PROFILE
+// globaltimer stamps of system 0: [cluster rank][step][0: own work done, 1: past the barrier]  (tools/micro/fused_bench.cu)
+__device__ unsigned long long fused_stamps[16][48][2];
+__device__ __forceinline__ unsigned long long fused_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FUSED_STAMP(I, W) do { if (threadIdx.x == 0 && blockIdx.y == 0) fused_stamps[rank][I][W] = fused_now(); } while (0)
+#else
+#define FUSED_STAMP(I, W) do { } while (0)
+#endif
+
 enum : int { FOP_LEAF = 0, FOP_GEMM = 1 };
 enum : int { FT_32x32 = 0, FT_32x64 = 1, FT_64x128 = 2, FT_128x128 = 3 };
 
@@ -188,6 +201,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_factor_kernel(const __
     const int b = blockIdx.y;
     double* mats[2] = {p.A + (int64_t)b * p.stride, p.Linv + (int64_t)b * p.stride};
 
+    FUSED_STAMP(p.n_ops, 0);
     for (int i = 0; i < p.n_ops; i++) {
         const FusedOp& op = p.ops[i];
         if (op.type == FOP_LEAF) {
@@ -212,10 +226,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_factor_kernel(const __
 #undef EXQ_FUSED_DISPATCH
             }
         }
+        FUSED_STAMP(i, 0);
         if (op.sync_after) {
             __threadfence();
             cluster.sync();
         }
+        FUSED_STAMP(i, 1);
     }
 }
 

@@ -254,14 +254,48 @@ __device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& 
     return !tile_skipped(a.lower_only, I, J);
 }
 
+// Shared-memory ring of gemm_kernel: stages of GEMM_HK bytes of k.  With 64-byte stages (the variance kernel's layout) the
+// 7-digit operands leave room for two stages only (86 KB in flight).  Stages of 32 bytes (ONE UMMA k step, SWIZZLE_32B)
+// are half as large, so five (S = 7) or six (S = 6) of them fit -- measured SLOWER on B200 (tools/micro/ozaki_gemm_test.cu,
+// n = 2048, 2 systems: 69 against 86 TFLOP/s FP64-equivalent for the node products, 46 against 57 for LAUUM): boxes with
+// 32-byte rows halve what every TMA request moves, and the producer becomes the limiter.  Kept as a compile-time option.
+#ifndef EXQ_OZ_GEMM_HK
+#define EXQ_OZ_GEMM_HK 64
+#endif
+constexpr int GEMM_HK = EXQ_OZ_GEMM_HK;
+static_assert(GEMM_HK == 32 || GEMM_HK == 64, "k bytes per stage: 32 or 64");
+template <int S>
+struct GCfg {
+    static constexpr int A_BYTES = S * BLK_C * GEMM_HK;
+    static constexpr int B_BYTES = S * BLK_R * GEMM_HK;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (227 * 1024 - 1280) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int TMEM_COLS = 512;
+};
+// K-major SWIZZLE_32B shared-memory matrix descriptor (rows of 32 B, 8-row groups 256 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                      // SWIZZLE_32B
+    return d;
+}
+__device__ __forceinline__ uint64_t gemm_smem_desc(uint32_t saddr) {
+    return GEMM_HK == 64 ? smem_desc_sw64(saddr) : smem_desc_sw32(saddr);
+}
+
 // GK: -1 plain GEMM; EXQ_KERNEL_MATERN52 / EXQ_KERNEL_SQEXP: cmode C_GRAD is available (fused gradient contraction)
 // (320 threads are budgeted as 384 by the register allocator: 168 registers per thread is the hardware limit here --
 // a launch with 192 fails with "too many resources" -- so the gradient epilogue lives with ~200 bytes of spills)
 template <int S, int GK = -1>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GArgs a) {
-    using C = Cfg<S>;
+    using C = GCfg<S>;
     constexpr int STAGES = C::STAGES;
+    constexpr int HALVES = BLK_K / GEMM_HK;       // ring stages per 64-byte k block of the tile walk
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -302,12 +336,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 int b, I, J, lo, hi;
                 if (!decode_gemm_item(a, i, b, I, J)) continue;
                 tile_krange(a.krange, I, J, nkb, lo, hi);
-                for (int kb = lo; kb < hi; kb++) {
+                for (int kh = lo * HALVES; kh < hi * HALVES; kh++) {
                     mbar_wait_guard(&empty[st], ph ^ 1u);
                     mbar_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
                     uint8_t* sa = smem + st * C::STAGE_BYTES;
-                    tma_load_3d(sa, &map_a, kb * BLK_K, b * a.M + I * BLK_C, 0, &full[st]);
-                    tma_load_3d(sa + C::A_BYTES, &map_b, kb * BLK_K, b * a.N + J * BLK_R, 0, &full[st]);
+                    tma_load_3d(sa, &map_a, kh * GEMM_HK, b * a.M + I * BLK_C, 0, &full[st]);
+                    tma_load_3d(sa + C::A_BYTES, &map_b, kh * GEMM_HK, b * a.N + J * BLK_R, 0, &full[st]);
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
             }
@@ -322,14 +356,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 tile_krange(a.krange, I, J, nkb, lo, hi);
                 mbar_wait_guard(tmem_empty, acc_ph ^ 1u);
                 tc_fence_after();
-                for (int kb = lo; kb < hi; kb++) {
+                for (int kh = lo * HALVES; kh < hi * HALVES; kh++) {
                     mbar_wait_guard(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + st * C::STAGE_BYTES);
-                    const uint64_t da0 = smem_desc_sw64(sa);
-                    const uint64_t db0 = smem_desc_sw64(sa + C::A_BYTES);
+                    const uint64_t da0 = gemm_smem_desc(sa);
+                    const uint64_t db0 = gemm_smem_desc(sa + C::A_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
+                    for (int ks = 0; ks < GEMM_HK / UMMA_K; ks++) {
 #pragma unroll
                         for (int p = 0; p < S; p++) {
                             // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE
@@ -337,18 +371,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                             // diagonals p+q .. p+q+m-1 are adjacent TMEM column blocks, so the 128-row tile is read
                             // from shared memory once per 4 products instead of once per product (at N = 64 the
                             // operand reads, 192 B/clk, exceed what shared memory delivers)
-                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
-                            const uint32_t accumulate = (kb > lo || ks > 0 || p > 0) ? 1u : 0u;
+                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * GEMM_HK) + ks * UMMA_K) >> 4);
+                            const uint32_t accumulate = (kh > lo * HALVES || ks > 0 || p > 0) ? 1u : 0u;
 #pragma unroll
                             for (int q = 0; q + p < S; q += 4) {
                                 const int m = (S - p - q) < 4 ? (S - p - q) : 4;
-                                const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
+                                const uint64_t db = db0 + (uint64_t)((q * (BLK_R * GEMM_HK) + ks * UMMA_K) >> 4);
                                 umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
                             }
                         }
                     }
                     umma_commit(&empty[st]);
-                    if (kb == hi - 1) umma_commit(tmem_full);
+                    if (kh == hi * HALVES - 1) umma_commit(tmem_full);
                     if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
                 acc_ph ^= 1u;
@@ -545,11 +579,11 @@ __global__ void grad_reduce_slots_kernel(const double* __restrict__ partial, int
 
 template <int S>
 inline cudaError_t set_gemm_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<S, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<S, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GCfg<S>::SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, GCfg<S>::SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+        e = cudaFuncSetAttribute(gemm_kernel<S, EXQ_KERNEL_SQEXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GCfg<S>::SMEM_BYTES);
     return e;
 }
 
@@ -583,18 +617,18 @@ inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs
                        int grad_kernel_id = -1) {
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C))) return rc;
-    if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R))) return rc;
+    if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C, GEMM_HK))) return rc;
+    if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R, GEMM_HK))) return rc;
     const int items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
     const int grid = items < sm_count ? items : sm_count;
     if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_MATERN52)
-        gemm_kernel<S, EXQ_KERNEL_MATERN52><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+        gemm_kernel<S, EXQ_KERNEL_MATERN52><<<grid, THREADS, GCfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
     else if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_SQEXP)
-        gemm_kernel<S, EXQ_KERNEL_SQEXP><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+        gemm_kernel<S, EXQ_KERNEL_SQEXP><<<grid, THREADS, GCfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
     else if (a.cmode == C_GRAD)
         return -1;
     else
-        gemm_kernel<S, -1><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
+        gemm_kernel<S, -1><<<grid, THREADS, GCfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
     return 0;
 }
 

@@ -382,15 +382,18 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // planes[S][rows][cols] int8 -> 3-D map {cols, rows, S}, box {64, box_rows, S}, SWIZZLE_64B
-inline int make_plane_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t cols, int S, int box_rows) {
+// box_k: k bytes per box = swizzle span (64: SWIZZLE_64B, 32: SWIZZLE_32B)
+inline int make_plane_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t cols, int S, int box_rows,
+                          int box_k = BLK_K) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return -1;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)S};
     cuuint64_t strides[2] = {(cuuint64_t)cols, (cuuint64_t)(rows * cols)};
-    cuuint32_t box[3] = {(cuuint32_t)BLK_K, (cuuint32_t)box_rows, (cuuint32_t)S};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, (cuuint32_t)S};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
