@@ -452,7 +452,7 @@ bool oz_planes_fit(const Sys& s, int digits, int M, int N, int K, bool same) {
 
 bool oz_gemm_wanted(const Sys& s, int M, int N, int K, bool same = false) {
     return !g.oz_off && (g.oz_factor_slices == 6 || g.oz_factor_slices == 7) && K >= g.oz_min_k && K <= 16384 &&
-           (M % 128) == 0 && (N % 64) == 0 && (K % 64) == 0 && (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count &&
+           (M % 128) == 0 && (N % 64) == 0 && (K % oz::OZ_KB) == 0 && (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count &&
            oz_planes_fit(s, g.oz_factor_slices, M, N, K, same);
 }
 

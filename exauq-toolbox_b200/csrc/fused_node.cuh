@@ -54,7 +54,10 @@ struct FusedOp {
 
 constexpr int FUSED_MAX_OPS = 40;          // a 1024-block: 8 leaves + 7 nodes x 4
 constexpr int FUSED_THREADS = 256;
-constexpr int FUSED_STAGES = 3;
+// cp.async stages per tile shape: as many as fit the budget, at most 16 (the whole k extent of a 256-wide node).  With
+// three stages every 16-wide k tile of a step waited for its own L2 round trip: a 128 x 128 x 128 step took 6-7 us of
+// which 2 us are DMMA time (tools/micro/fused_bench.cu).
+constexpr int FUSED_GEMM_BUDGET = 200 * 1024;
 
 struct FusedArgs {
     double* A;
@@ -67,8 +70,14 @@ struct FusedArgs {
 
 constexpr int fused_tile_bm(int t) { return t == FT_128x128 ? 128 : t == FT_64x128 ? 64 : 32; }
 constexpr int fused_tile_bn(int t) { return t == FT_128x128 || t == FT_64x128 ? 128 : t == FT_32x64 ? 64 : 32; }
-constexpr int FUSED_GEMM_SMEM = FUSED_STAGES * (128 + 128) * GEMM_LDS_K * (int)sizeof(double);
-constexpr int FUSED_SMEM_BYTES = (LEAF_SMEM_BYTES > FUSED_GEMM_SMEM ? LEAF_SMEM_BYTES : FUSED_GEMM_SMEM);
+__host__ __device__ constexpr int fused_stage_bytes(int bm, int bn) {
+    // A tile bm x 16 (k-contiguous, padded) + B tile: bn x 16 padded or 16 x (bn + 4): the larger of the two layouts
+    return (bm * GEMM_LDS_K + (bn * GEMM_LDS_K > GEMM_BK * (bn + 4) ? bn * GEMM_LDS_K : GEMM_BK * (bn + 4))) * (int)sizeof(double);
+}
+__host__ __device__ constexpr int fused_stages(int bm, int bn) {
+    return FUSED_GEMM_BUDGET / fused_stage_bytes(bm, bn) > 16 ? 16 : FUSED_GEMM_BUDGET / fused_stage_bytes(bm, bn);
+}
+constexpr int FUSED_SMEM_BYTES = (LEAF_SMEM_BYTES > FUSED_GEMM_BUDGET ? LEAF_SMEM_BYTES : FUSED_GEMM_BUDGET);
 
 // One BM x BN output tile with all 256 threads (8 warps 2 x 4), k range [kt_lo, kt_hi) in units of 16.
 template <int BL, int BM, int BN>
@@ -76,6 +85,8 @@ __device__ __forceinline__ void fused_gemm_tile(const double* __restrict__ A, co
                                                 double* __restrict__ C, int64_t ld, int m0, int n0, int kt_lo, int kt_hi,
                                                 int cmode, double* smem) {
     constexpr int WN = 4, MF = BM / 2 / 8, NF = BN / WN / 8;
+    constexpr int FUSED_STAGES = fused_stages(BM, BN);
+    static_assert(FUSED_STAGES >= 3, "tile too large for the shared-memory budget");
     constexpr int A_ELEMS = BM * GEMM_LDS_K;
     constexpr int B_LD_MN = BN + 4;
     constexpr int B_ELEMS = (BL == LAYOUT_K) ? BN * GEMM_LDS_K : GEMM_BK * B_LD_MN;

@@ -54,10 +54,12 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
     double c[LEAF_SLOTS][2];
 #pragma unroll
     for (int s = 0; s < LEAF_SLOTS; s++) {
-        int q = (warp - 1) + LEAF_OWNERS * s;
-        int bj = 0, rem = q;
-        while (rem >= LEAF_NBLK - bj && bj < LEAF_NBLK) { rem -= LEAF_NBLK - bj; bj++; }
-        int bi = bj + rem;
+        // tile q of the column-major enumeration of the 136 lower tiles: column bj starts at off(bj) = 16 bj - bj (bj - 1) / 2
+        const int q = (warp - 1) + LEAF_OWNERS * s;
+        int bj = (int)((33.0f - sqrtf(1089.0f - 8.0f * (float)min(q, 135))) * 0.5f);
+        if (16 * (bj + 1) - ((bj + 1) * bj) / 2 <= q) bj++;
+        if (16 * bj - (bj * (bj - 1)) / 2 > q) bj--;
+        const int bi = bj + q - (16 * bj - (bj * (bj - 1)) / 2);
         tb[s] = (warp > 0 && q < 136) ? ((bi << 8) | bj) : -1;
     }
     // all 17 tile loads of a thread are issued before the first one is consumed (the index search above used to sit
@@ -133,6 +135,50 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
     // look-ahead -- warp 0 factors diagonal block p + 1 WHILE the other warps (and warp 0 afterwards) apply the
     // rank-8 update to the rest of the trailing matrix (c2).  The 8-pivot chain (1400 cycles) used to be a phase of
     // its own with 7 warps idle: 22 k of the leaf's 80 k cycles.
+    // Block row i of X = L^-1 (tiles X_ij, j < i), by the tile-owning warps: X_ij = -XD_i * sum_{k=j}^{i-1} L_ik X_kj with
+    // X_jj = XD_j.  Row i needs block row i of L, XD_i and the rows above it -- all there once step i's panel phase is
+    // done -- so it runs in the shadow of warp 0's pivot chain instead of as a phase of its own after the factorisation
+    // (12 k of the leaf's 74 k cycles).  Column j always belongs to the same warp; finished tiles are parked TRANSPOSED in
+    // the strictly upper part of S, where that warp reads them back as DMMA B fragments.
+    double* my_scratch = scratch + warp * 8 * LEAF_XD_LD;
+    auto x_row = [&](int i) {
+#pragma unroll 1
+        for (int j = warp - 1; j < i; j += LEAF_OWNERS) {
+            // Y = sum_k L_ik X_kj, two independent accumulators (even / odd k)
+            double y0[2] = {0.0, 0.0}, y1[2] = {0.0, 0.0};
+            {
+                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * j + t];
+                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * j + 4 + t];
+                const double b0 = XD[(j * 8 + t) * LEAF_XD_LD + g];
+                const double b1 = XD[(j * 8 + 4 + t) * LEAF_XD_LD + g];
+                dmma884(y0[0], y0[1], a0, b0);
+                dmma884(y1[0], y1[1], a1, b1);
+            }
+#pragma unroll 2
+            for (int k = j + 1; k < i; k++) {
+                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * k + t];
+                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * k + 4 + t];
+                const double b0 = S[(8 * j + g) * LEAF_LD + 8 * k + t];
+                const double b1 = S[(8 * j + g) * LEAF_LD + 8 * k + 4 + t];
+                dmma884(y0[0], y0[1], a0, b0);
+                dmma884(y1[0], y1[1], a1, b1);
+            }
+            // X_ij = -XD_i * Y : Y goes through scratch to become a B fragment
+            my_scratch[g * LEAF_XD_LD + 2 * t] = y0[0] + y1[0];
+            my_scratch[g * LEAF_XD_LD + 2 * t + 1] = y0[1] + y1[1];
+            __syncwarp();
+            const double b0 = my_scratch[t * LEAF_XD_LD + g];
+            const double b1 = my_scratch[(4 + t) * LEAF_XD_LD + g];
+            const double a0 = XD[(i * 8 + g) * LEAF_XD_LD + t];
+            const double a1 = XD[(i * 8 + g) * LEAF_XD_LD + 4 + t];
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, -a0, b0);
+            dmma884(d0, d1, -a1, b1);
+            S[(8 * j + 2 * t) * LEAF_LD + 8 * i + g] = d0;
+            S[(8 * j + 2 * t + 1) * LEAF_LD + 8 * i + g] = d1;
+            __syncwarp();
+        }
+    };
     if (warp == 0) diag_factor(0);
     __syncthreads();
     LEAF_TICK(1);
@@ -229,6 +275,7 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
             if (p + 1 < LEAF_NBLK) diag_factor(j0 + 8);
         } else {
             LEAF_ALL_SLOTS(smin2 < 0 ? 0 : smin2, false)
+            if (p > 0) x_row(p);
         }
 #undef LEAF_ALL_SLOTS
 #undef LEAF_SLOT_UPDATE
@@ -236,74 +283,33 @@ __device__ __forceinline__ void leaf_body(double* __restrict__ A, double* __rest
         LEAF_TICK(3);
     }
 
-    // ================= phase 2: Linv = L^-1 ==============================================
-    // Block column j of X = L^-1 depends only on L and on the diagonal inverses XD:
-    //   X_jj = XD_j,   X_ij = -XD_i * sum_{k=j}^{i-1} L_ik X_kj   (i > j),
-    // so each warp solves its own block columns {w, 15 - w} (17 block rows in total for every
-    // warp) with no block-wide barrier; finished X_kj tiles are parked TRANSPOSED in the strictly
-    // upper part of S, where the same warp reads them back as DMMA B fragments.
-    double* my_scratch = scratch + warp * 8 * LEAF_XD_LD;
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        const int j = half ? (LEAF_NBLK - 1 - warp) : warp;
-#pragma unroll 1
-        for (int i = j + 1; i < LEAF_NBLK; i++) {
-            // Y = sum_k L_ik X_kj, two independent accumulators (even / odd k)
-            double y0[2] = {0.0, 0.0}, y1[2] = {0.0, 0.0};
-            {
-                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * j + t];
-                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * j + 4 + t];
-                const double b0 = XD[(j * 8 + t) * LEAF_XD_LD + g];
-                const double b1 = XD[(j * 8 + 4 + t) * LEAF_XD_LD + g];
-                dmma884(y0[0], y0[1], a0, b0);
-                dmma884(y1[0], y1[1], a1, b1);
-            }
-#pragma unroll 2
-            for (int k = j + 1; k < i; k++) {
-                const double a0 = S[(8 * i + g) * LEAF_LD + 8 * k + t];
-                const double a1 = S[(8 * i + g) * LEAF_LD + 8 * k + 4 + t];
-                const double b0 = S[(8 * j + g) * LEAF_LD + 8 * k + t];
-                const double b1 = S[(8 * j + g) * LEAF_LD + 8 * k + 4 + t];
-                dmma884(y0[0], y0[1], a0, b0);
-                dmma884(y1[0], y1[1], a1, b1);
-            }
-            // X_ij = -XD_i * Y : Y goes through scratch to become a B fragment
-            my_scratch[g * LEAF_XD_LD + 2 * t] = y0[0] + y1[0];
-            my_scratch[g * LEAF_XD_LD + 2 * t + 1] = y0[1] + y1[1];
-            __syncwarp();
-            const double b0 = my_scratch[t * LEAF_XD_LD + g];
-            const double b1 = my_scratch[(4 + t) * LEAF_XD_LD + g];
-            const double a0 = XD[(i * 8 + g) * LEAF_XD_LD + t];
-            const double a1 = XD[(i * 8 + g) * LEAF_XD_LD + 4 + t];
-            double d0 = 0.0, d1 = 0.0;
-            dmma884(d0, d1, -a0, b0);
-            dmma884(d0, d1, -a1, b1);
-            S[(8 * j + 2 * t) * LEAF_LD + 8 * i + g] = d0;
-            S[(8 * j + 2 * t + 1) * LEAF_LD + 8 * i + g] = d1;
-            __syncwarp();
-        }
-    }
     LEAF_TICK(5);
     __syncthreads();
 
     // ---- write back L (upper zeroed) and Linv (full tile, zeros above the diagonal), 16 bytes per store ----
     for (int idx = tid; idx < LEAF_N * (LEAF_N / 2); idx += LEAF_THREADS) {
         const int r = idx >> 6, cc = (idx & 63) << 1;
-        double2 l, x;
+        double2 l;
         l.x = (cc <= r) ? S[r * LEAF_LD + cc] : 0.0;
         l.y = (cc + 1 <= r) ? S[r * LEAF_LD + cc + 1] : 0.0;
         *reinterpret_cast<double2*>(A + (int64_t)r * ld + cc) = l;
-        const int br = r >> 3, bc = cc >> 3;          // cc and cc + 1 lie in the same 8-column block
+    }
+    // Linv tile by tile (a warp per 8 x 8 tile, lane (g, t) holds row g, columns 2t, 2t+1): the parked tiles are read
+    // along their shared-memory rows (a row-major sweep of the output read them with a stride of 2 LD doubles: 16-way
+    // bank conflicts, half of the write-back's 8.9 k cycles)
+    for (int tile = warp; tile < LEAF_NBLK * LEAF_NBLK; tile += LEAF_THREADS / 32) {
+        const int br = tile >> 4, bc = tile & 15;
+        double2 x;
         if (bc < br) {
-            x.x = S[cc * LEAF_LD + r];
-            x.y = S[(cc + 1) * LEAF_LD + r];
+            x.x = S[(8 * bc + 2 * t) * LEAF_LD + 8 * br + g];
+            x.y = S[(8 * bc + 2 * t + 1) * LEAF_LD + 8 * br + g];
         } else if (bc == br) {
-            x.x = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7)];
-            x.y = XD[(br * 8 + (r & 7)) * LEAF_XD_LD + (cc & 7) + 1];
+            x.x = XD[(br * 8 + g) * LEAF_XD_LD + 2 * t];
+            x.y = XD[(br * 8 + g) * LEAF_XD_LD + 2 * t + 1];
         } else {
             x.x = x.y = 0.0;
         }
-        *reinterpret_cast<double2*>(Li + (int64_t)r * ld + cc) = x;
+        *reinterpret_cast<double2*>(Li + (int64_t)(8 * br + g) * ld + 8 * bc + 2 * t) = x;
     }
     LEAF_TICK(6);
     __syncthreads();   // shared memory is free again for the caller

@@ -221,7 +221,9 @@ inline int64_t gemm_kblocks(int M, int N, int K, int krange, int lower_only) {
             if (tile_skipped(lower_only, I, J)) continue;
             int lo, hi;
             tile_krange(krange, I, J, nkb, lo, hi);
-            if (hi > lo) total += hi - lo;
+            if (hi <= lo) continue;
+            // the kernel walks whole 128-byte blocks: ranges are widened to even 64-byte boundaries
+            total += EXQ_OZ_K128 ? 2 * (((hi + 1) >> 1) - (lo >> 1)) : hi - lo;
         }
     return total;
 }
@@ -254,38 +256,9 @@ __device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& 
     return !tile_skipped(a.lower_only, I, J);
 }
 
-// Shared-memory ring of gemm_kernel: stages of GEMM_HK bytes of k.  With 64-byte stages (the variance kernel's layout) the
-// 7-digit operands leave room for two stages only (86 KB in flight).  Stages of 32 bytes (ONE UMMA k step, SWIZZLE_32B)
-// are half as large, so five (S = 7) or six (S = 6) of them fit -- measured SLOWER on B200 (tools/micro/ozaki_gemm_test.cu,
-// n = 2048, 2 systems: 69 against 86 TFLOP/s FP64-equivalent for the node products, 46 against 57 for LAUUM): boxes with
-// 32-byte rows halve what every TMA request moves, and the producer becomes the limiter.  Kept as a compile-time option.
-#ifndef EXQ_OZ_GEMM_HK
-#define EXQ_OZ_GEMM_HK 64
-#endif
-constexpr int GEMM_HK = EXQ_OZ_GEMM_HK;
-static_assert(GEMM_HK == 32 || GEMM_HK == 64, "k bytes per stage: 32 or 64");
+constexpr int GEMM_STATIC_SMEM = 6 * 1024;                   // gx_s / ga_s of the gradient epilogue + slack
 template <int S>
-struct GCfg {
-    static constexpr int A_BYTES = S * BLK_C * GEMM_HK;
-    static constexpr int B_BYTES = S * BLK_R * GEMM_HK;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (227 * 1024 - 1280) / STAGE_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr int TMEM_COLS = 512;
-};
-// K-major SWIZZLE_32B shared-memory matrix descriptor (rows of 32 B, 8-row groups 256 B apart)
-__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(256 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)6 << 61;                      // SWIZZLE_32B
-    return d;
-}
-__device__ __forceinline__ uint64_t gemm_smem_desc(uint32_t saddr) {
-    return GEMM_HK == 64 ? smem_desc_sw64(saddr) : smem_desc_sw32(saddr);
-}
+using GCfg = KCfg<S, GEMM_STATIC_SMEM>;
 
 // GK: -1 plain GEMM; EXQ_KERNEL_MATERN52 / EXQ_KERNEL_SQEXP: cmode C_GRAD is available (fused gradient contraction)
 // (320 threads are budgeted as 384 by the register allocator: 168 registers per thread is the hardware limit here --
@@ -294,16 +267,22 @@ template <int S, int GK = -1>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GArgs a) {
     using C = GCfg<S>;
-    constexpr int STAGES = C::STAGES;
-    constexpr int HALVES = BLK_K / GEMM_HK;       // ring stages per 64-byte k block of the tile walk
+    using C64 = Cfg<S>;
+    constexpr bool K128 = EXQ_OZ_K128 != 0;
+    constexpr int STAGES = K128 ? C::NB : C64::STAGES;      // stages of the (B or combined) ring
+    constexpr int NA = K128 ? C::NA : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    // K128: [NA A slots][NB B stages][barriers]; else [STAGES combined stages][barriers]
+    uint8_t* smem_b = smem + (K128 ? NA * C::A_SLOT : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(K128 ? smem_b + C::NB * C::B_STAGE : smem + STAGES * C64::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    uint64_t* full_a = bars + 2 * STAGES + 2;                // [NA]
+    uint64_t* empty_a = full_a + NA;                         // [NA]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_a + NA);
 
     // fused gradient epilogue: the tile's 64 columns (pre-scaled coordinates, alpha), shared by the epilogue warps
     __shared__ __align__(16) double gx_s[(GK >= 0 ? GRAD_D : 2) * (GK >= 0 ? BLK_R : 1)];
@@ -318,6 +297,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
+        for (int s = 0; s < NA; s++) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&empty_a[s], 1);
+        }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, EPI_WARPS);
         fence_mbar_init();
@@ -330,60 +313,107 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     if (warp == 0) {
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
+            int st = 0, sa_i = 0;
+            uint32_t ph = 0, pha = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int b, I, J, lo, hi;
                 if (!decode_gemm_item(a, i, b, I, J)) continue;
                 tile_krange(a.krange, I, J, nkb, lo, hi);
-                for (int kh = lo * HALVES; kh < hi * HALVES; kh++) {
-                    mbar_wait_guard(&empty[st], ph ^ 1u);
-                    mbar_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
-                    uint8_t* sa = smem + st * C::STAGE_BYTES;
-                    tma_load_3d(sa, &map_a, kh * GEMM_HK, b * a.M + I * BLK_C, 0, &full[st]);
-                    tma_load_3d(sa + C::A_BYTES, &map_b, kh * GEMM_HK, b * a.N + J * BLK_R, 0, &full[st]);
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                if (K128) {
+                    // 128-byte k blocks: the range is widened to whole blocks (the extra 64 bytes lie beyond the operand's
+                    // triangle, where the slicers wrote zero digits)
+                    for (int kb = lo >> 1; kb < (hi + 1) >> 1; kb++) {
+                        mbar_wait_guard(&empty[st], ph ^ 1u);
+                        mbar_expect_tx(&full[st], (uint32_t)C::B_STAGE);
+                        tma_load_3d(smem_b + st * C::B_STAGE, &map_b, kb * 128, b * a.N + J * BLK_R, 0, &full[st]);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+#pragma unroll 1
+                        for (int p = 0; p < S; p++) {
+                            mbar_wait_guard(&empty_a[sa_i], pha ^ 1u);
+                            mbar_expect_tx(&full_a[sa_i], (uint32_t)C::A_SLOT);
+                            tma_load_3d(smem + sa_i * C::A_SLOT, &map_a, kb * 128, b * a.M + I * BLK_C, p, &full_a[sa_i]);
+                            if (++sa_i == NA) { sa_i = 0; pha ^= 1u; }
+                        }
+                    }
+                } else {
+                    for (int kb = lo; kb < hi; kb++) {
+                        mbar_wait_guard(&empty[st], ph ^ 1u);
+                        mbar_expect_tx(&full[st], (uint32_t)C64::STAGE_BYTES);
+                        uint8_t* sa = smem + st * C64::STAGE_BYTES;
+                        tma_load_3d(sa, &map_a, kb * BLK_K, b * a.M + I * BLK_C, 0, &full[st]);
+                        tma_load_3d(sa + C64::A_BYTES, &map_b, kb * BLK_K, b * a.N + J * BLK_R, 0, &full[st]);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0, acc_ph = 0;
+            int st = 0, sa_i = 0;
+            uint32_t ph = 0, pha = 0, acc_ph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int b, I, J, lo, hi;
                 if (!decode_gemm_item(a, i, b, I, J)) continue;
                 tile_krange(a.krange, I, J, nkb, lo, hi);
                 mbar_wait_guard(tmem_empty, acc_ph ^ 1u);
                 tc_fence_after();
-                for (int kh = lo * HALVES; kh < hi * HALVES; kh++) {
-                    mbar_wait_guard(&full[st], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + st * C::STAGE_BYTES);
-                    const uint64_t da0 = gemm_smem_desc(sa);
-                    const uint64_t db0 = gemm_smem_desc(sa + C::A_BYTES);
-#pragma unroll
-                    for (int ks = 0; ks < GEMM_HK / UMMA_K; ks++) {
+                // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE MMA of N = 64 m:
+                // those digit tiles are contiguous in shared memory and their diagonals p+q .. p+q+m-1 are adjacent TMEM
+                // column blocks, so the 128-row tile is read from shared memory once per 4 products instead of once per
+                // product (at N = 64 the operand reads, 192 B/clk, exceed what shared memory delivers)
+                if (K128) {
+                    const int kb0 = lo >> 1, kb1 = (hi + 1) >> 1;
+                    for (int kb = kb0; kb < kb1; kb++) {
+                        mbar_wait_guard(&full[st], ph);
+                        const uint64_t db0 = smem_desc_sw128(smem_u32(smem_b + st * C::B_STAGE));
 #pragma unroll
                         for (int p = 0; p < S; p++) {
-                            // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE
-                            // MMA of N = 64 m: those digit tiles are contiguous in shared memory and their
-                            // diagonals p+q .. p+q+m-1 are adjacent TMEM column blocks, so the 128-row tile is read
-                            // from shared memory once per 4 products instead of once per product (at N = 64 the
-                            // operand reads, 192 B/clk, exceed what shared memory delivers)
-                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * GEMM_HK) + ks * UMMA_K) >> 4);
-                            const uint32_t accumulate = (kh > lo * HALVES || ks > 0 || p > 0) ? 1u : 0u;
+                            mbar_wait_guard(&full_a[sa_i], pha);
+                            tc_fence_after();
+                            const uint64_t da0 = smem_desc_sw128(smem_u32(smem + sa_i * C::A_SLOT));
 #pragma unroll
-                            for (int q = 0; q + p < S; q += 4) {
-                                const int m = (S - p - q) < 4 ? (S - p - q) : 4;
-                                const uint64_t db = db0 + (uint64_t)((q * (BLK_R * GEMM_HK) + ks * UMMA_K) >> 4);
-                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                            for (int ks = 0; ks < 128 / UMMA_K; ks++) {
+                                const uint64_t da = da0 + (uint64_t)((ks * UMMA_K) >> 4);
+                                const uint32_t accumulate = (kb > kb0 || ks > 0 || p > 0) ? 1u : 0u;
+#pragma unroll
+                                for (int q = 0; q + p < S; q += 4) {
+                                    const int m = (S - p - q) < 4 ? (S - p - q) : 4;
+                                    const uint64_t db = db0 + (uint64_t)((q * (BLK_R * 128) + ks * UMMA_K) >> 4);
+                                    umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                                }
+                            }
+                            umma_commit(&empty_a[sa_i]);
+                            if (++sa_i == NA) { sa_i = 0; pha ^= 1u; }
+                        }
+                        umma_commit(&empty[st]);
+                        if (kb == kb1 - 1) umma_commit(tmem_full);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+                    }
+                } else {
+                    for (int kb = lo; kb < hi; kb++) {
+                        mbar_wait_guard(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + st * C64::STAGE_BYTES);
+                        const uint64_t da0 = smem_desc_sw64(sa);
+                        const uint64_t db0 = smem_desc_sw64(sa + C64::A_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
+#pragma unroll
+                            for (int p = 0; p < S; p++) {
+                                const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                                const uint32_t accumulate = (kb > lo || ks > 0 || p > 0) ? 1u : 0u;
+#pragma unroll
+                                for (int q = 0; q + p < S; q += 4) {
+                                    const int m = (S - p - q) < 4 ? (S - p - q) : 4;
+                                    const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
+                                    umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                                }
                             }
                         }
+                        umma_commit(&empty[st]);
+                        if (kb == hi - 1) umma_commit(tmem_full);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
                     }
-                    umma_commit(&empty[st]);
-                    if (kh == hi * HALVES - 1) umma_commit(tmem_full);
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
                 acc_ph ^= 1u;
             }
@@ -431,8 +461,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
                 for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + half * 32 + c0), d[u]);
                 tmem_ld_wait();
+                if (c0 == 16) {
+                    // the last raw values are in registers: TMEM goes back BEFORE they are recombined
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
+                    // diagonals u = 0..3 (weights 256^-2 .. 256^-5) and u = 4..S-1, each combined exactly
                     int64_t hi = 0, lo = 0;
 #pragma unroll
                     for (int u = 0; u < 4 && u < S; u++) hi = hi * (1 << W) + (int64_t)d[u][c];
@@ -443,9 +480,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     z[c0 + c] = v;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
             // phase 2: scale and write the FP64 tile row
 #pragma unroll
             for (int c = 0; c < 32; c++) z[c] = z[c] * row_scale * pow2d(__ldg(eb + c));
@@ -617,8 +651,10 @@ inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs
                        int grad_kernel_id = -1) {
     CUtensorMap ma, mb;
     int rc;
-    if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C, GEMM_HK))) return rc;
-    if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R, GEMM_HK))) return rc;
+    if (EXQ_OZ_K128 && (a.K % 128)) return -2;
+    // K128: one digit tile of the 128-row operand per box, all S digit tiles of the 64-row operand per box
+    if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C, OZ_KB, EXQ_OZ_K128 ? 1 : S))) return rc;
+    if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R, OZ_KB, S))) return rc;
     const int items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
     const int grid = items < sm_count ? items : sm_count;
     if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_MATERN52)

@@ -192,6 +192,53 @@ __host__ __device__ constexpr uint32_t idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Shared-memory rings of the two tcgen05 kernels.
+//
+// Round-2 layout (EXQ_OZ_K128 = 0, Cfg<S>): stages of 64 bytes of k holding all S digits of both operands, SWIZZLE_64B.  At
+// S = 7 a stage is 86 KB, two fit, and ncu showed the tensor pipe 70 % active.  A ring of 32-byte stages (five fit) measured
+// SLOWER, 69 against 86 TFLOP/s FP64-equivalent at n = 2048 (tools/micro/ozaki_gemm_test.cu), which pointed at the cause: the
+// TMA unit pays per ROW of a box (~1.3 cycles per row per SM whether the row is 32 or 64 bytes), so a 64-byte stage of 1344
+// rows needs ~1800 cycles to land plus the L2 round trip -- more than the ~2000 cycles its MMAs take when only two stages
+// exist; and 64-byte rows use half the width of a shared-memory write.
+//
+// Current layout (EXQ_OZ_K128 = 1, KCfg<S>): k blocks of 128 bytes (SWIZZLE_128B, rows as wide as shared memory: half the rows
+// per byte), and TWO rings so that they still fit: the S digit tiles of the 64-row operand of a k block form a stage
+// (S x 8 KB, two stages), the digit tiles of the 128-row operand -- each is used by the MMAs of ONE digit p and then dead --
+// stream through a ring of 16 KB slots (six to eight of them) with a barrier pair per slot.  Node products of the recursion
+// 91 -> 97 TFLOP/s FP64-equivalent, LAUUM 71 -> 75 (n = 2048, 15 systems).
+#ifndef EXQ_OZ_K128
+#define EXQ_OZ_K128 1
+#endif
+constexpr int OZ_KB = EXQ_OZ_K128 ? 128 : BLK_K;     // k bytes per block of the pipeline
+template <int S, int STATIC_SMEM = 0>
+struct KCfg {
+    // A slot = one digit tile of the 128-row operand; B stage = S digit tiles of the 64-row operand
+    static constexpr int A_SLOT = BLK_C * 128;
+    static constexpr int B_STAGE = S * BLK_R * 128;
+    static constexpr int NB = 2;
+    static constexpr int NA = (227 * 1024 - 1280 - STATIC_SMEM - NB * B_STAGE) / A_SLOT;
+    static constexpr int K128_BYTES = NA * A_SLOT + NB * B_STAGE;
+    static constexpr int SMEM_BYTES = (EXQ_OZ_K128 ? K128_BYTES : Cfg<S>::STAGES * Cfg<S>::STAGE_BYTES) + 1024 + 256;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(NA >= 4, "A ring too short");
+};
+// The variance kernel takes the split rings only where the 64-byte layout is short of stages: S = 7 gains 4.5 % (4.85 ->
+// 4.64 ms per 32768-candidate chunk at Np = 4096), S = 6 with its three 64-byte stages is 2 % faster as it was (3.55 ms).
+template <int S>
+__host__ __device__ constexpr bool var_k128() { return EXQ_OZ_K128 != 0 && S >= 7; }
+template <int S>
+__host__ __device__ constexpr int var_smem_bytes() { return var_k128<S>() ? KCfg<S>::K128_BYTES + 1024 + 256 : Cfg<S>::SMEM_BYTES; }
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+    return d;
+}
+
 struct Args {
     const int* row_exp;   // exponent of every Linv row
     double* P;            // [2 Np / 64][ldp] column sums of squares per half row block (32 rows of Linv)
@@ -217,16 +264,23 @@ __device__ __forceinline__ int item_count(int n_ctile, int n_rblk) { return n_ct
 template <int S>
 __global__ void __launch_bounds__(THREADS, 1)
 colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_l, Args a) {
-    using C = Cfg<S>;
-    constexpr int STAGES = C::STAGES;
+    using C = KCfg<S>;
+    using C64 = Cfg<S>;
+    constexpr bool K128 = var_k128<S>();
+    constexpr int STAGES = K128 ? C::NB : C64::STAGES;      // stages of the (Linv-side or combined) ring
+    constexpr int NA = K128 ? C::NA : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    // K128: [NA candidate digit tiles][NB Linv stages][barriers]; else [STAGES combined stages][barriers]
+    uint8_t* smem_b = smem + (K128 ? NA * C::A_SLOT : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(K128 ? smem_b + C::NB * C::B_STAGE : smem + STAGES * C64::STAGE_BYTES);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + STAGES;       // [STAGES]
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    uint64_t* full_a = bars + 2 * STAGES + 2;   // [NA]
+    uint64_t* empty_a = full_a + NA;            // [NA]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_a + NA);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = item_count(a.n_ctile, a.n_rblk);
@@ -235,6 +289,10 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < NA; s++) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&empty_a[s], 1);
         }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, EPI_WARPS);
@@ -249,59 +307,105 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
+            int st = 0, sa_i = 0;
+            uint32_t ph = 0, pha = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int ct, j;
                 decode_item(i, a.n_ctile, a.n_rblk, ct, j);
-                for (int kb = 0; kb <= j; kb++) {
-                    mbar_wait_guard(&empty[st], ph ^ 1u);
-                    mbar_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
-                    uint8_t* sa = smem + st * C::STAGE_BYTES;
-                    tma_load_3d(sa, &map_c, kb * BLK_K, ct * BLK_C, 0, &full[st]);
-                    tma_load_3d(sa + C::A_BYTES, &map_l, kb * BLK_K, j * BLK_R, 0, &full[st]);
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
+                if (K128) {
+                    // 128-byte k blocks 0 .. j/2 (for even j the second half lies above Linv's diagonal: zero digits)
+                    for (int kb = 0; kb <= (j >> 1); kb++) {
+                        mbar_wait_guard(&empty[st], ph ^ 1u);
+                        mbar_expect_tx(&full[st], (uint32_t)C::B_STAGE);
+                        tma_load_3d(smem_b + st * C::B_STAGE, &map_l, kb * 128, j * BLK_R, 0, &full[st]);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+#pragma unroll 1
+                        for (int p = 0; p < S; p++) {
+                            mbar_wait_guard(&empty_a[sa_i], pha ^ 1u);
+                            mbar_expect_tx(&full_a[sa_i], (uint32_t)C::A_SLOT);
+                            tma_load_3d(smem + sa_i * C::A_SLOT, &map_c, kb * 128, ct * BLK_C, p, &full_a[sa_i]);
+                            if (++sa_i == NA) { sa_i = 0; pha ^= 1u; }
+                        }
+                    }
+                } else {
+                    for (int kb = 0; kb <= j; kb++) {
+                        mbar_wait_guard(&empty[st], ph ^ 1u);
+                        mbar_expect_tx(&full[st], (uint32_t)C64::STAGE_BYTES);
+                        uint8_t* sa = smem + st * C64::STAGE_BYTES;
+                        tma_load_3d(sa, &map_c, kb * BLK_K, ct * BLK_C, 0, &full[st]);
+                        tma_load_3d(sa + C64::A_BYTES, &map_l, kb * BLK_K, j * BLK_R, 0, &full[st]);
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0, acc_ph = 0;
+            int st = 0, sa_i = 0;
+            uint32_t ph = 0, pha = 0, acc_ph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int ct, j;
                 decode_item(i, a.n_ctile, a.n_rblk, ct, j);
                 mbar_wait_guard(tmem_empty, acc_ph ^ 1u);   // epilogue has drained the previous item's accumulators
                 tc_fence_after();
-                for (int kb = 0; kb <= j; kb++) {
-                    mbar_wait_guard(&full[st], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + st * C::STAGE_BYTES);
-                    const uint64_t da0 = smem_desc_sw64(sa);
-                    const uint64_t db0 = smem_desc_sw64(sa + C::A_BYTES);
-#pragma unroll
-                    for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
+                // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE MMA of N = 64 m:
+                // those digit tiles are contiguous in shared memory and their diagonals p+q .. p+q+m-1 are adjacent TMEM
+                // column blocks, so the 128-row tile is read from shared memory once per 4 products instead of once per
+                // product (at N = 64 the operand reads, 192 B/clk, exceed what shared memory delivers)
+                if (K128) {
+                    const int kb1 = (j >> 1) + 1;
+                    for (int kb = 0; kb < kb1; kb++) {
+                        mbar_wait_guard(&full[st], ph);
+                        const uint64_t db0 = smem_desc_sw128(smem_u32(smem_b + st * C::B_STAGE));
 #pragma unroll
                         for (int p = 0; p < S; p++) {
-                            // digit p of the 128-row operand against digits q .. q+m-1 of the 64-row operand in ONE
-                            // MMA of N = 64 m: those digit tiles are contiguous in shared memory and their
-                            // diagonals p+q .. p+q+m-1 are adjacent TMEM column blocks, so the 128-row tile is read
-                            // from shared memory once per 4 products instead of once per product (at N = 64 the
-                            // operand reads, 192 B/clk, exceed what shared memory delivers)
-                            const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
-                            const uint32_t accumulate = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;
+                            mbar_wait_guard(&full_a[sa_i], pha);
+                            tc_fence_after();
+                            const uint64_t da0 = smem_desc_sw128(smem_u32(smem + sa_i * C::A_SLOT));
 #pragma unroll
-                            for (int q = 0; q + p < S; q += 4) {
-                                const int m = (S - p - q) < 4 ? (S - p - q) : 4;
-                                const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
-                                umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                            for (int ks = 0; ks < 128 / UMMA_K; ks++) {
+                                const uint64_t da = da0 + (uint64_t)((ks * UMMA_K) >> 4);
+                                const uint32_t accumulate = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;
+#pragma unroll
+                                for (int q = 0; q + p < S; q += 4) {
+                                    const int m = (S - p - q) < 4 ? (S - p - q) : 4;
+                                    const uint64_t db = db0 + (uint64_t)((q * (BLK_R * 128) + ks * UMMA_K) >> 4);
+                                    umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                                }
+                            }
+                            umma_commit(&empty_a[sa_i]);             // slot reusable once these MMAs have read it
+                            if (++sa_i == NA) { sa_i = 0; pha ^= 1u; }
+                        }
+                        umma_commit(&empty[st]);
+                        if (kb == kb1 - 1) umma_commit(tmem_full);   // accumulators complete
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
+                    }
+                } else {
+                    for (int kb = 0; kb <= j; kb++) {
+                        mbar_wait_guard(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + st * C64::STAGE_BYTES);
+                        const uint64_t da0 = smem_desc_sw64(sa);
+                        const uint64_t db0 = smem_desc_sw64(sa + C64::A_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < BLK_K / UMMA_K; ks++) {
+#pragma unroll
+                            for (int p = 0; p < S; p++) {
+                                const uint64_t da = da0 + (uint64_t)((p * (BLK_C * BLK_K) + ks * UMMA_K) >> 4);
+                                const uint32_t accumulate = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;
+#pragma unroll
+                                for (int q = 0; q + p < S; q += 4) {
+                                    const int m = (S - p - q) < 4 ? (S - p - q) : 4;
+                                    const uint64_t db = db0 + (uint64_t)((q * (BLK_R * BLK_K) + ks * UMMA_K) >> 4);
+                                    umma_i8(tmem_base + (uint32_t)((p + q) * BLK_R), da, db, idesc_i8(BLK_C, BLK_R * m), accumulate);
+                                }
                             }
                         }
+                        umma_commit(&empty[st]);                 // stage reusable once these MMAs have read it
+                        if (kb == j) umma_commit(tmem_full);     // accumulators complete
+                        if (++st == STAGES) { st = 0; ph ^= 1u; }
                     }
-                    umma_commit(&empty[st]);                 // stage reusable once these MMAs have read it
-                    if (kb == j) umma_commit(tmem_full);     // accumulators complete
-                    if (++st == STAGES) { st = 0; ph ^= 1u; }
                 }
                 acc_ph ^= 1u;
             }
@@ -327,6 +431,12 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
 #pragma unroll
                 for (int u = 0; u < S; u++) tmem_ld16(tmem_base + lane_base + (uint32_t)(u * BLK_R + half * 32 + c0), d[u]);
                 tmem_ld_wait();
+                if (c0 == 16) {
+                    // the last raw values are in registers: TMEM goes back BEFORE they are recombined
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     // diagonals u = 0..3 (weights 256^-2 .. 256^-5) and u = 4..S-1, each combined exactly
@@ -340,9 +450,6 @@ colsumsq_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                     z[c0 + c] = v;
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
             // phase 2
             double sum = 0.0;
             const int* re = a.row_exp + j * BLK_R + half * 32;
@@ -382,17 +489,18 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // planes[S][rows][cols] int8 -> 3-D map {cols, rows, S}, box {64, box_rows, S}, SWIZZLE_64B
-// box_k: k bytes per box = swizzle span (64: SWIZZLE_64B, 32: SWIZZLE_32B)
+// box_k: k bytes per box = swizzle span (128 / 64 / 32); box_planes: digit planes per box (default: all S)
 inline int make_plane_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t cols, int S, int box_rows,
-                          int box_k = BLK_K) {
+                          int box_k = BLK_K, int box_planes = 0) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return -1;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)S};
     cuuint64_t strides[2] = {(cuuint64_t)cols, (cuuint64_t)(rows * cols)};
-    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, (cuuint32_t)S};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, (cuuint32_t)(box_planes > 0 ? box_planes : S)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -400,7 +508,7 @@ inline int make_plane_map(CUtensorMap* map, const int8_t* planes, int64_t rows, 
 
 template <int S>
 inline cudaError_t set_attrs() {
-    return cudaFuncSetAttribute(colsumsq_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<S>::SMEM_BYTES);
+    return cudaFuncSetAttribute(colsumsq_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, var_smem_bytes<S>());
 }
 
 // P[2 j + h][c] = sum over rows 32 h .. 32 h + 31 of block j of (Linv k_c)^2, from sliced operands.
@@ -410,14 +518,17 @@ inline int launch_colsumsq(const int8_t* cand_planes, int Mc, int cand_exp, cons
                            int Np, double* P, int64_t ldp, int sm_count, cudaStream_t stream) {
     CUtensorMap mc, ml;
     int rc;
-    if ((rc = make_plane_map(&mc, cand_planes, Mc, Np, S, BLK_C))) return rc;
-    if ((rc = make_plane_map(&ml, linv_planes, Np, Np, S, BLK_R))) return rc;
+    constexpr bool K128 = var_k128<S>();
+    if (K128 && (Np % 128)) return -2;
+    // K128: one candidate digit tile per box, all S digit tiles of the Linv rows per box
+    if ((rc = make_plane_map(&mc, cand_planes, Mc, Np, S, BLK_C, K128 ? 128 : BLK_K, K128 ? 1 : S))) return rc;
+    if ((rc = make_plane_map(&ml, linv_planes, Np, Np, S, BLK_R, K128 ? 128 : BLK_K, S))) return rc;
     Args a{};
     a.row_exp = row_exp; a.P = P; a.ldp = ldp; a.n_ctile = Mc / BLK_C; a.n_rblk = Np / BLK_R;
     a.out_scale = std::ldexp(1.0, 2 * cand_exp - 2 * W * 5);   // (2^f 256^-5)^2
     const int items = a.n_ctile * a.n_rblk;
     const int grid = items < sm_count ? items : sm_count;
-    colsumsq_kernel<S><<<grid, THREADS, Cfg<S>::SMEM_BYTES, stream>>>(mc, ml, a);
+    colsumsq_kernel<S><<<grid, THREADS, var_smem_bytes<S>(), stream>>>(mc, ml, a);
     return 0;
 }
 

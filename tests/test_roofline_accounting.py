@@ -12,7 +12,8 @@ import pytest
 
 from exauq_toolbox_b200 import _lib
 
-BLK_C, BLK_R, BLK_K = 128, 64, 64        # output tile rows / columns, k bytes per block (ozaki_i8.cuh)
+BLK_C, BLK_R, BLK_K = 128, 64, 64        # output tile rows / columns, k bytes per counted block (ozaki_i8.cuh)
+PIPE_K = 128                             # the kernels walk k in blocks of 128 bytes: ranges widen to whole blocks
 KR_FULL, KR_LE_J, KR_GE_J, KR_LE_I, KR_GE_I = range(5)
 
 
@@ -35,7 +36,10 @@ def kblocks(M, N, K, krange, lower_only):
                 hi = min(nkb, rows[1] // BLK_K + 1)
             elif krange == KR_GE_I:
                 lo = rows[0] // BLK_K
-            total += max(0, hi - lo)
+            if hi > lo:
+                # first and last 128-byte block that hold a kept 64-byte block, counted in 64-byte units
+                first, last = (lo * BLK_K) // PIPE_K, ((hi - 1) * BLK_K) // PIPE_K
+                total += (last - first + 1) * (PIPE_K // BLK_K)
     return total
 
 

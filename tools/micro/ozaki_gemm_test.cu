@@ -1,7 +1,7 @@
 // Stand-alone check of the int8 tcgen05 tile GEMM (ozaki_gemm.cuh) in the five operand
 // configurations the potrf+trtri recursion and LAUUM use, against a host FP64 reference.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o build/ozaki_gemm_test tools/micro/ozaki_gemm_test.cu
-//   ozaki_gemm_test <n> <B> [time_n]
+//   ozaki_gemm_test <n> <B> [time_n] [time_B]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -115,6 +115,7 @@ int run_case(const Case& c, int n, int B, int ld, const std::vector<double>& hA,
 int main(int argc, char** argv) {
     const int n = argc > 1 ? atoi(argv[1]) : 256, B = argc > 2 ? atoi(argv[2]) : 2;
     const int tn = argc > 3 ? atoi(argv[3]) : 0;
+    const int tB = argc > 4 ? atoi(argv[4]) : B;
     int sm = 0;
     CK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0));
     CK(oz::set_gemm_attrs<6>());
@@ -129,6 +130,7 @@ int main(int argc, char** argv) {
     int rc = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int nn = pass == 0 ? n : tn;
+        const int B = pass == 0 ? atoi(argc > 2 ? argv[2] : "2") : tB;
         if (nn <= 0) continue;
         const int ld = nn + 128;   // sub-matrix inside a larger system
         std::mt19937_64 rng(7);

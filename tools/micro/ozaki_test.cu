@@ -31,8 +31,9 @@ int run(int Np, int Mc, int mode, int reps, const std::vector<double>& hL, const
     CK(cudaMalloc(&lp, (size_t)S * Np * Np));
     CK(cudaMalloc(&cp, (size_t)S * Mc * Np));
     CK(cudaMalloc(&rexp, Np * sizeof(int)));
-    CK(cudaMalloc(&P, (size_t)nrb * Mc * 8));
-    CK(cudaMemset(P, 0xff, (size_t)nrb * Mc * 8));
+    // the int8 kernel writes TWO partials per 64-row block (one per 32-row half: P[2 j + half][cand])
+    CK(cudaMalloc(&P, (size_t)2 * nrb * Mc * 8));
+    CK(cudaMemset(P, 0xff, (size_t)2 * nrb * Mc * 8));
     CK(oz::set_attrs<S>());
     int sm = 0;
     CK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0));
@@ -60,8 +61,10 @@ int run(int Np, int Mc, int mode, int reps, const std::vector<double>& hL, const
         }
     }
     ms_slice /= reps; ms_main /= reps;
-    std::vector<double> hP((size_t)nrb * Mc);
-    CK(cudaMemcpy(hP.data(), P, hP.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> hP2((size_t)2 * nrb * Mc), hP((size_t)nrb * Mc);
+    CK(cudaMemcpy(hP2.data(), P, hP2.size() * 8, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < nrb; j++)
+        for (int c = 0; c < Mc; c++) hP[(size_t)j * Mc + c] = hP2[(size_t)(2 * j) * Mc + c] + hP2[(size_t)(2 * j + 1) * Mc + c];
     // compare per-candidate totals (what the variance uses) and per-block partials
     double max_rel_tot = 0, max_abs_tot = 0, max_rel_blk = 0;
     int bad = 0;
