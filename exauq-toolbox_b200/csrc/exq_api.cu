@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,6 +60,7 @@ struct Ctx {
     size_t kct_elems = 0, p_elems = 0;
     double* PMR = nullptr;           // [2][Np/64][chunk] partial means / repulsion products of the fused PEI pipeline
     size_t pmr_elems = 0;
+    int oz_sched = 1;                // EXQ_OZ_SCHED=0: arithmetic tile walk of the int8 GEMM instead of the balanced work lists
     int grad_fused = 1;              // EXQ_GRAD_FUSED=0: K^-1 stored by LAUUM and contracted by a separate gradient kernel
     int pei_fused = 1;               // EXQ_PEI_FUSED=0: round-1 pipeline (FP64 chunk -> slicer -> per-candidate epilogue)
     // int8 tcgen05 variance path (ozaki_i8.cuh): digits per operand (EXQ_OZAKI_SLICES = 0 keeps the FP64 DMMA
@@ -462,6 +465,51 @@ bool factor_uses_int8(const Sys& s) {
     return n2 > 0 && (oz_gemm_wanted(s, n2, n1, n1) || oz_gemm_wanted(s, n2, n2, n1, true) || oz_gemm_wanted(s, n2, n1, n2));
 }
 
+// ---- balanced work lists of the int8 GEMM (oz::make_schedule), one per launch shape, kept on the device ----------------
+struct SchedEntry {
+    const uint32_t* dev = nullptr;
+    int n = 0, grid = 0;
+};
+std::map<std::array<int, 7>, SchedEntry> g_sched;
+uint32_t* g_sched_arena = nullptr;
+size_t g_sched_cap = 0, g_sched_used = 0;          // in entries
+
+// false: no list (arena unavailable) -- the kernel then walks the tiles arithmetically
+bool sched_get(int M, int N, int K, int B, int krange, int lower_only, SchedEntry& e) {
+    if (!g.oz_sched) return false;
+    const int items = (M / oz::BLK_C) * (N / oz::BLK_R) * B;
+    const int grid = std::min(items, g.sm_count);
+    const std::array<int, 7> key{M, N, K, B, krange, lower_only, grid};
+    auto it = g_sched.find(key);
+    if (it != g_sched.end()) { e = it->second; return true; }
+    if (!g_sched_arena) {
+        g_sched_cap = (size_t)8 << 20;             // 32 MB of 4-byte entries
+        if (cudaMalloc(&g_sched_arena, g_sched_cap * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            g_sched_arena = nullptr; g_sched_cap = 0;
+            return false;
+        }
+    }
+    std::vector<uint32_t> list;
+    oz::make_schedule(M, N, K, B, krange, lower_only, grid, list);
+    if (list.size() > g_sched_cap) return false;
+    if (g_sched_used + list.size() > g_sched_cap) {   // arena full: every launch that reads the old lists must be done
+        cudaStreamSynchronize(g.stream);
+        g_sched.clear();
+        g_sched_used = 0;
+    }
+    uint32_t* dst = g_sched_arena + g_sched_used;
+    if (cudaMemcpyAsync(dst, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaStreamSynchronize(g.stream);               // once per shape; the host vector goes out of scope
+    g_sched_used += list.size();
+    e.dev = dst; e.n = (int)list.size(); e.grid = grid;
+    g_sched[key] = e;
+    return true;
+}
+
 template <int S>
 int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
               int cmode, double fl, bool reuse_a, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
@@ -483,6 +531,8 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
     if (ga) a.g = *ga;
+    SchedEntry se;
+    if (sched_get(M, N, K, s.B, krange, lower_only, se)) { a.sched = se.dev; a.n_sched = se.n; a.sched_grid = se.grid; }
     a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
     // int8 operations issued: every non-skipped (128 x 64) tile runs S(S+1)/2 digit products over its k range --
     // counted by the same tile walk the kernel does (round 1 counted LAUUM twice: 2/3 instead of 1/3 of the cube)
@@ -1106,6 +1156,7 @@ int exq_init(int device) {
     }
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
+    if (const char* e = getenv("EXQ_OZ_SCHED")) g.oz_sched = atoi(e) != 0;
     if (const char* e = getenv("EXQ_PEI_FUSED")) g.pei_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_GRAD_FUSED")) g.grad_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_FUSE_N")) { const int v = atoi(e); g.fuse_n = (v >= 256 && v <= 1024) ? (v / 128) * 128 : 0; }
@@ -1134,6 +1185,9 @@ int exq_shutdown(void) {
     sys_pool_clear();
     if (g_cand_parked) { cand_free_buffers(g_cand_parked); delete g_cand_parked; g_cand_parked = nullptr; }
     cudaFree(g.KcT); cudaFree(g.P); cudaFree(g.cand_planes); cudaFree(g.PMR);
+    cudaFree(g_sched_arena);
+    g_sched_arena = nullptr; g_sched_cap = g_sched_used = 0;
+    g_sched.clear();
     plane_pool_clear();
     for (auto ev : g.pool) cudaEventDestroy(ev);
     g.pool.clear();

@@ -11,6 +11,9 @@
 //
 //   C[i][j] (op)= sum_k A(i, k) * B(j, k)     i < M, j < N, k in a per-tile range (KR_*)
 #pragma once
+#include <algorithm>
+#include <vector>
+
 #include "gemm_dmma.cuh"   // KR_*, C_* enums
 #include "ozaki_i8.cuh"
 
@@ -198,7 +201,11 @@ struct GArgs {
     int krange, lower_only, cmode;
     int heavy_last;       // tiles with larger I (or J) carry more k blocks: walk the tile list backwards
     int sys_slow;         // 1: systems are the slow index of the work list (see decode_gemm_item)
+    const uint32_t* sched;   // balanced work list (make_schedule): entry i is the item of CTA i % grid in round i / grid,
+    int n_sched;             // packed (system << 20 | I << 10 | J), SCHED_NONE = idle; nullptr: the arithmetic walk above
+    int sched_grid;          // CTAs the list was dealt to
 };
+constexpr uint32_t SCHED_NONE = 0xffffffffu;
 
 // k-block range [lo, hi) of output tile (I: 128 rows, J: 64 columns)
 __host__ __device__ __forceinline__ void tile_krange(int krange, int I, int J, int nkb, int& lo, int& hi) {
@@ -256,6 +263,62 @@ __device__ __forceinline__ bool decode_gemm_item(const GArgs& a, int item, int& 
     return !tile_skipped(a.lower_only, I, J);
 }
 
+// item i of this launch: from the balanced list when there is one
+__device__ __forceinline__ bool gemm_item(const GArgs& a, int i, int& b, int& I, int& J) {
+    if (a.sched) {
+        const uint32_t it = __ldg(a.sched + i);
+        if (it == SCHED_NONE) return false;
+        b = (int)(it >> 20); I = (int)((it >> 10) & 1023u); J = (int)(it & 1023u);
+        return true;
+    }
+    return decode_gemm_item(a, i, b, I, J);
+}
+
+// Balanced static schedule.  The arithmetic walk hands item i to CTA i % grid whatever the item weighs: tiles skipped by
+// lower_only are holes in the list and the k range of a tile varies 1 : 32 across a triangular product, so the busiest CTA
+// carried 7 % (L21, T), 23 % (SYRK) and 6-38 % (LAUUM) more k blocks than the average (15 systems, n = 2048 / 4096).  Here the
+// kept tiles of each system are sorted by weight, systems stay in sequence (their digit planes share L2), and every round
+// of `grid` items is dealt heaviest-first to the CTAs with the least work so far: the loads end within ~1 % of each other.
+// Deterministic (a pure function of the shape), so results stay reproducible run to run.
+inline void make_schedule(int M, int N, int K, int B, int krange, int lower_only, int grid, std::vector<uint32_t>& out) {
+    const int nI = M / BLK_C, nJ = N / BLK_R, nkb = K / BLK_K;
+    struct It { uint32_t id; float w; };
+    std::vector<It> all;
+    all.reserve((size_t)nI * nJ * B);
+    std::vector<It> sys;
+    for (int b = 0; b < B; b++) {
+        sys.clear();
+        for (int I = 0; I < nI; I++)
+            for (int J = 0; J < nJ; J++) {
+                if (tile_skipped(lower_only, I, J)) continue;
+                int lo, hi;
+                tile_krange(krange, I, J, nkb, lo, hi);
+                if (hi <= lo) { lo = 0; hi = 0; }
+                // 128-byte k blocks plus about one block's worth of fill + epilogue hand-over per tile
+                const float w = (float)(EXQ_OZ_K128 ? ((hi + 1) >> 1) - (lo >> 1) : (hi - lo) * 0.5f) + 1.0f;
+                sys.push_back({((uint32_t)b << 20) | ((uint32_t)I << 10) | (uint32_t)J, w});
+            }
+        std::stable_sort(sys.begin(), sys.end(), [](const It& x, const It& y) { return x.w > y.w; });
+        all.insert(all.end(), sys.begin(), sys.end());
+    }
+    const size_t rounds = (all.size() + grid - 1) / grid;
+    out.assign(rounds * grid, SCHED_NONE);
+    std::vector<float> load(grid, 0.0f);
+    std::vector<int> order(grid);
+    std::vector<It> win;
+    for (size_t r = 0; r < rounds; r++) {
+        const size_t lo = r * grid, hi = std::min(all.size(), lo + grid);
+        win.assign(all.begin() + lo, all.begin() + hi);
+        std::stable_sort(win.begin(), win.end(), [](const It& x, const It& y) { return x.w > y.w; });
+        for (int c = 0; c < grid; c++) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return load[x] < load[y]; });
+        for (size_t k = 0; k < win.size(); k++) {
+            out[lo + order[k]] = win[k].id;
+            load[order[k]] += win[k].w;
+        }
+    }
+}
+
 constexpr int GEMM_STATIC_SMEM = 6 * 1024;                   // gx_s / ga_s of the gradient epilogue + slack
 template <int S>
 using GCfg = KCfg<S, GEMM_STATIC_SMEM>;
@@ -289,7 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     __shared__ double ga_s[GK >= 0 ? BLK_R : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
+    const int n_items = a.sched ? a.n_sched : (a.M / BLK_C) * (a.N / BLK_R) * a.B;
     const int nkb = a.K / BLK_K;
 
     if (threadIdx.x == 0) {
@@ -317,7 +380,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             uint32_t ph = 0, pha = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int b, I, J, lo, hi;
-                if (!decode_gemm_item(a, i, b, I, J)) continue;
+                if (!gemm_item(a, i, b, I, J)) continue;
                 tile_krange(a.krange, I, J, nkb, lo, hi);
                 if (K128) {
                     // 128-byte k blocks: the range is widened to whole blocks (the extra 64 bytes lie beyond the operand's
@@ -353,7 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             uint32_t ph = 0, pha = 0, acc_ph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
                 int b, I, J, lo, hi;
-                if (!decode_gemm_item(a, i, b, I, J)) continue;
+                if (!gemm_item(a, i, b, I, J)) continue;
                 tile_krange(a.krange, I, J, nkb, lo, hi);
                 mbar_wait_guard(tmem_empty, acc_ph ^ 1u);
                 tc_fence_after();
@@ -444,7 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int k = 0; k < GD + 2; k++) gacc[k] = 0.0;
         for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
             int b, I, J;
-            if (!decode_gemm_item(a, i, b, I, J)) continue;
+            if (!gemm_item(a, i, b, I, J)) continue;
             const int row = I * BLK_C + quarter * 32 + lane;
             // 2^(ea - 40): row scale and the weight 256^-5 of the high diagonal group
             const double row_scale = pow2d(__ldg(a.expA + (int64_t)b * a.M + row) - 2 * W * 5 / 2);
@@ -656,7 +719,7 @@ inline int launch_gemm(const int8_t* planesA, const int8_t* planesB, const GArgs
     if ((rc = make_plane_map(&ma, planesA, (int64_t)a.B * a.M, a.K, S, BLK_C, OZ_KB, EXQ_OZ_K128 ? 1 : S))) return rc;
     if ((rc = make_plane_map(&mb, planesB, (int64_t)a.B * a.N, a.K, S, BLK_R, OZ_KB, S))) return rc;
     const int items = (a.M / BLK_C) * (a.N / BLK_R) * a.B;
-    const int grid = items < sm_count ? items : sm_count;
+    const int grid = a.sched ? a.sched_grid : (items < sm_count ? items : sm_count);
     if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_MATERN52)
         gemm_kernel<S, EXQ_KERNEL_MATERN52><<<grid, THREADS, GCfg<S>::SMEM_BYTES, stream>>>(ma, mb, a);
     else if (a.cmode == C_GRAD && grad_kernel_id == EXQ_KERNEL_SQEXP)

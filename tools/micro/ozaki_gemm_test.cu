@@ -47,7 +47,17 @@ int run_case(const Case& c, int n, int B, int ld, const std::vector<double>& hA,
     a.expA = eA; a.expB = eB; a.C = dC; a.ldc = ld; a.strideC = sq; a.M = n; a.N = n; a.K = n; a.B = B;
     a.krange = c.krange; a.lower_only = c.lower_only; a.cmode = c.cmode;
     a.heavy_last = (c.krange == KR_LE_J || c.krange == KR_LE_I) ? 1 : 0;
-    a.sys_slow = c.lower_only ? 0 : 1;
+    a.sys_slow = 1;
+    uint32_t* dsched = nullptr;
+    if (getenv("OZ_SCHED") && atoi(getenv("OZ_SCHED"))) {
+        std::vector<uint32_t> list;
+        const int items = (n / oz::BLK_C) * (n / oz::BLK_R) * B;
+        const int grid = items < sm ? items : sm;
+        oz::make_schedule(n, n, n, B, c.krange, c.lower_only, grid, list);
+        CK(cudaMalloc(&dsched, list.size() * 4));
+        CK(cudaMemcpy(dsched, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+        a.sched = dsched; a.n_sched = (int)list.size(); a.sched_grid = grid;
+    }
     float ms_s = 0, ms_g = 0;
     const int reps = check ? 1 : 3;
     for (int r = 0; r < reps; r++) {
@@ -108,7 +118,7 @@ int run_case(const Case& c, int n, int B, int ld, const std::vector<double>& hA,
            bad ? "** MISMATCH **" : "ok", ms_s, ms_g, fl / (ms_g * 1e-3) / 1e12);
     if (check) printf(", max err / (max|a_i| max|b_j|) = %.2e", worst);
     printf("\n");
-    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(planes); cudaFree(exps);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(planes); cudaFree(exps); cudaFree(dsched);
     return bad ? 1 : 0;
 }
 
