@@ -74,7 +74,9 @@ struct Ctx {
     // int8 path for the large GEMMs of the potrf+trtri recursion and LAUUM (ozaki_gemm.cuh): 7 digits = 56 bits
     // keeps the factorisation at the FP64 level (EXQ_OZAKI_FACTOR_SLICES = 0: FP64 DMMA everywhere)
     int oz_factor_slices = 7;
-    int oz_min_k = 1024;             // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K)
+    int oz_min_k = 512;              // smallest inner dimension that goes to the int8 kernel (EXQ_OZAKI_MIN_K); with the balanced
+                                     // work lists the 1024-row nodes (k = 512) are faster there than on FP64 DMMA (47 -> 5.6 + 16 + 13 ms
+                                     // of DMMA / int8 / slicing time per design batch)
     int fast_corr = 1;               // branch-free exp / sqrt + compile-time kernel id in the assembly kernel (EXQ_FAST_CORR)
     int oz_lauum_slices = 6;         // K^-1 = Linv^T Linv for the gradient (parity 1e-7): 48 bits unless the guard widens
     // ---- conditioning guard of the int8 paths ----------------------------------------------------------------

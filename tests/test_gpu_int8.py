@@ -63,7 +63,9 @@ def test_int8_matches_dmma_at_full_size(exq, orc, n, d, r):
     assert np.all(ref["info"] == 0)
     # defaults (variance 6 digits, factorisation 7) far inside BASELINE.json's tolerances; 6 digits in the
     # factorisation only just meet them (log-likelihood 1e-10, mean 5e-10), which is why 7 is the default
-    for vd, fd, tol_nll, tol_mean, tol_var, tol_grad in [(6, 7, 1e-12, 1e-9, 1e-9, 1e-8), (7, 6, 1e-9, 1e-8, 1e-8, 1e-6)]:
+    # (with the nodes of 1024 rows on the int8 kernel too -- three levels of 7-digit products at n = 4096 -- the
+    # log-likelihood sits 3e-12 from the FP64 DMMA value; BASELINE.json asks for 1e-9)
+    for vd, fd, tol_nll, tol_mean, tol_var, tol_grad in [(6, 7, 1e-11, 1e-9, 1e-9, 1e-8), (7, 6, 1e-9, 1e-8, 1e-8, 1e-6)]:
         exq._lib.set_int8_digits(vd, fd)
         got = _evaluate(exq, X, y, Xc, corr_raw, thetas)
         assert np.all(got["info"] == 0)
