@@ -105,8 +105,12 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     if (lane == 0) row_exp[(int64_t)b * rows + row] = e;
     const double sc = pow2d(8 * S - e);
     int8_t* orow = out + ((int64_t)b * rows + row) * K;
+    // The kernels read a masked operand only inside the (128-byte aligned) k range of the tile the row belongs to: zero
+    // digits are needed from the diagonal to the end of its 128-block (MASK_LE) or from the start of it (MASK_GE), not over
+    // the whole row -- the rest of the planes is never read (tile_krange) and is left as it is.
+    const int w_lo = mask == MASK_GE ? (row & ~127) : 0, w_hi = mask == MASK_LE ? min(K, (row & ~127) + 128) : K;
     // 4 consecutive elements per lane: 1 KB contiguous per warp on the way in, 128 B per plane on the way out
-    for (int k0 = lane << 2; k0 < K; k0 += 128) {
+    for (int k0 = w_lo + (lane << 2); k0 < w_hi; k0 += 128) {
         uint32_t packed[S];
 #pragma unroll
         for (int p = 0; p < S; p++) packed[p] = 0u;
@@ -138,6 +142,9 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double* __restric
     const int row = r0 + rr;
     // tiles entirely outside the kept triangle are all zeros
     const bool any = mask == MASK_NONE || (mask == MASK_LE ? k0 <= r0 + 63 : k0 + 63 >= r0);
+    // tiles outside the kept triangle: zero digits only inside the 128-block of the diagonal, nothing beyond it is ever
+    // read (see slice_rows_kernel)
+    if (!any && (mask == MASK_LE ? k0 >= (r0 & ~127) + 128 : k0 + 64 <= (r0 & ~127))) return;
     const double sc = pow2d(8 * S - row_exp[(int64_t)b * rows + row]);
     const double* s = src + (int64_t)b * stride_sys;
 #pragma unroll
