@@ -60,6 +60,15 @@ struct Ctx {
     size_t kct_elems = 0, p_elems = 0;
     double* PMR = nullptr;           // [2][Np/64][chunk] partial means / repulsion products of the fused PEI pipeline
     size_t pmr_elems = 0;
+    int oz_min_tiles = 16;           // fewest 128 x 64 output tiles (over the batch) for the int8 kernel INSIDE exq_gp_logpost_batch
+                                     // (EXQ_OZAKI_MIN_TILES; -1: the SM count).  Even 32 CTAs finish a k = 512 product of one system faster
+                                     // than the FP64 DMMA kernel does (9 us + slicing against 46 us): a round of ONE system 4.72 -> 4.36 ms.
+                                     // A fit (one system, feeds predictions and the LOO sweep) keeps the SM-count rule: with all three
+                                     // levels on 7-digit products its LOO means at cond 4e7 sit 8 x further from the oracle than FP64's.
+    bool in_logpost = false;         // set while exq_gp_logpost_batch enqueues work
+    bool oz_shallow = false;         // set while a system whose kappa reached guard_widen is re-factored with the int8 kernel on
+                                     // the top levels only (k >= 1024, chip-filling batches): deeper 7-digit levels cost accuracy as
+                                     // conditioning worsens (kappa 1e8: log-posterior 5e-6 from the oracle against 2e-8)
     int oz_sched = 1;                // EXQ_OZ_SCHED=0: arithmetic tile walk of the int8 GEMM instead of the balanced work lists
     int grad_fused = 1;              // EXQ_GRAD_FUSED=0: K^-1 stored by LAUUM and contracted by a separate gradient kernel
     int pei_fused = 1;               // EXQ_PEI_FUSED=0: round-1 pipeline (FP64 chunk -> slicer -> per-candidate epilogue)
@@ -456,8 +465,10 @@ bool oz_planes_fit(const Sys& s, int digits, int M, int N, int K, bool same) {
 }
 
 bool oz_gemm_wanted(const Sys& s, int M, int N, int K, bool same = false) {
-    return !g.oz_off && (g.oz_factor_slices == 6 || g.oz_factor_slices == 7) && K >= g.oz_min_k && K <= 16384 &&
-           (M % 128) == 0 && (N % 64) == 0 && (K % oz::OZ_KB) == 0 && (int64_t)(M / 128) * (N / 64) * s.B >= g.sm_count &&
+    const bool deep = g.in_logpost && !g.oz_shallow;
+    return !g.oz_off && (g.oz_factor_slices == 6 || g.oz_factor_slices == 7) && K >= (deep ? g.oz_min_k : std::max(g.oz_min_k, 1024)) &&
+           K <= 16384 &&
+           (M % 128) == 0 && (N % 64) == 0 && (K % oz::OZ_KB) == 0 && (int64_t)(M / 128) * (N / 64) * s.B >= (deep && g.oz_min_tiles >= 0 ? g.oz_min_tiles : g.sm_count) &&
            oz_planes_fit(s, g.oz_factor_slices, M, N, K, same);
 }
 
@@ -1159,6 +1170,7 @@ int exq_init(int device) {
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
     if (const char* e = getenv("EXQ_OZ_SCHED")) g.oz_sched = atoi(e) != 0;
+    if (const char* e = getenv("EXQ_OZAKI_MIN_TILES")) g.oz_min_tiles = atoi(e);
     if (const char* e = getenv("EXQ_PEI_FUSED")) g.pei_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_GRAD_FUSED")) g.grad_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_FUSE_N")) { const int v = atoi(e); g.fuse_n = (v >= 256 && v <= 1024) ? (v / 128) * 128 : 0; }
@@ -1851,6 +1863,10 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
     Bmax = std::min(Bmax, R);
     int rc = sys_alloc(gp->batch, Bmax, N, d, true, false);
     if (rc) return rc;
+    struct InLogpost {
+        InLogpost() { g.in_logpost = true; }
+        ~InLogpost() { g.in_logpost = false; }
+    } in_logpost_scope;
     Sys& s = gp->batch;
     const int dmax = d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
     const int nt = Np / 128;
@@ -1928,17 +1944,28 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
             }
             if (!any) break;
         }
-        // conditioning guard: badly conditioned systems leave the int8 path
+        // conditioning guard: badly conditioned systems leave the int8 path (kappa >= guard_fallback) or keep it on the top
+        // levels only (kappa >= guard_widen)
         if (!rc && int8_factor) {
             bool redo = false;
+            const bool deep_rules = g.oz_min_k < 1024 || (g.oz_min_tiles >= 0 && g.oz_min_tiles < g.sm_count);
             for (int b = 0; b < B && !rc; b++) {
-                if (bad[b] || info[b] != 0 || kappa_of(b) < g.guard_fallback) continue;
-                g.guard_fallbacks++;
-                on_dmma[b] = 1;
-                g.oz_off = true;
+                if (bad[b] || info[b] != 0) continue;
+                const double kap = kappa_of(b);
+                if (kap >= g.guard_fallback) {
+                    g.guard_fallbacks++;
+                    on_dmma[b] = 1;
+                    g.oz_off = true;
+                } else if (kap >= g.guard_widen && deep_rules) {
+                    g.guard_widened++;
+                    g.oz_shallow = true;
+                } else {
+                    continue;
+                }
                 Sys v = sys_view(s, b, 1, dmax);
                 rc = enqueue_factor(gp, v, thb.data() + (size_t)b * (d + 2));
                 g.oz_off = false;
+                g.oz_shallow = false;
                 redo = true;
             }
             if (!rc && redo) rc = read_state();
