@@ -482,8 +482,9 @@ bool factor_uses_int8(const Sys& s) {
 struct SchedEntry {
     const uint32_t* dev = nullptr;
     int n = 0, grid = 0;
+    int built_for = 0, kept = 0;      // systems the list was built for, kept tiles per system
 };
-std::map<std::array<int, 7>, SchedEntry> g_sched;
+std::map<std::array<int, 6>, SchedEntry> g_sched;
 uint32_t* g_sched_arena = nullptr;
 size_t g_sched_cap = 0, g_sched_used = 0;          // in entries
 
@@ -492,34 +493,46 @@ bool sched_get(int M, int N, int K, int B, int krange, int lower_only, SchedEntr
     if (!g.oz_sched) return false;
     const int items = (M / oz::BLK_C) * (N / oz::BLK_R) * B;
     const int grid = std::min(items, g.sm_count);
-    const std::array<int, 7> key{M, N, K, B, krange, lower_only, grid};
+    const std::array<int, 6> key{M, N, K, krange, lower_only, grid};
     auto it = g_sched.find(key);
-    if (it != g_sched.end()) { e = it->second; return true; }
-    if (!g_sched_arena) {
-        g_sched_cap = (size_t)8 << 20;             // 32 MB of 4-byte entries
-        if (cudaMalloc(&g_sched_arena, g_sched_cap * sizeof(uint32_t)) != cudaSuccess) {
+    if (it == g_sched.end() || it->second.built_for < B) {
+        if (!g_sched_arena) {
+            g_sched_cap = (size_t)8 << 20;             // 32 MB of 4-byte entries
+            if (cudaMalloc(&g_sched_arena, g_sched_cap * sizeof(uint32_t)) != cudaSuccess) {
+                cudaGetLastError();
+                g_sched_arena = nullptr; g_sched_cap = 0;
+                return false;
+            }
+        }
+        // built for the next power of two: the batches of a MAP fit shrink restart by restart, and every prefix of a
+        // list is a balanced list (make_schedule), so one construction (1 ms for LAUUM at n = 4096, 16 systems) serves them all
+        int Bq = 1;
+        while (Bq < B) Bq <<= 1;
+        if (grid < g.sm_count) Bq = B;                 // fewer items than SMs: the grid depends on B itself
+        std::vector<uint32_t> list;
+        SchedEntry ne;
+        ne.kept = oz::make_schedule(M, N, K, Bq, krange, lower_only, grid, list);
+        if (list.size() > g_sched_cap) return false;
+        if (g_sched_used + list.size() > g_sched_cap) {   // arena full: every launch that reads the old lists must be done
+            cudaStreamSynchronize(g.stream);
+            g_sched.clear();
+            g_sched_used = 0;
+        }
+        uint32_t* dst = g_sched_arena + g_sched_used;
+        if (cudaMemcpyAsync(dst, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream) != cudaSuccess) {
             cudaGetLastError();
-            g_sched_arena = nullptr; g_sched_cap = 0;
             return false;
         }
+        cudaStreamSynchronize(g.stream);               // once per shape; the host vector goes out of scope
+        g_sched_used += list.size();
+        ne.dev = dst; ne.n = (int)list.size(); ne.grid = grid; ne.built_for = Bq;
+        g_sched[key] = ne;
+        it = g_sched.find(key);
     }
-    std::vector<uint32_t> list;
-    oz::make_schedule(M, N, K, B, krange, lower_only, grid, list);
-    if (list.size() > g_sched_cap) return false;
-    if (g_sched_used + list.size() > g_sched_cap) {   // arena full: every launch that reads the old lists must be done
-        cudaStreamSynchronize(g.stream);
-        g_sched.clear();
-        g_sched_used = 0;
-    }
-    uint32_t* dst = g_sched_arena + g_sched_used;
-    if (cudaMemcpyAsync(dst, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    cudaStreamSynchronize(g.stream);               // once per shape; the host vector goes out of scope
-    g_sched_used += list.size();
-    e.dev = dst; e.n = (int)list.size(); e.grid = grid;
-    g_sched[key] = e;
+    e = it->second;
+    // the rounds that hold the first B systems
+    const int64_t need = ((int64_t)B * e.kept + grid - 1) / grid * grid;
+    e.n = (int)std::min<int64_t>(e.n, need);
     return true;
 }
 

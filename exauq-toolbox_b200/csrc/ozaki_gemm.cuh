@@ -276,7 +276,7 @@ __device__ __forceinline__ bool gemm_item(const GArgs& a, int i, int& b, int& I,
         const uint32_t it = __ldg(a.sched + i);
         if (it == SCHED_NONE) return false;
         b = (int)(it >> 20); I = (int)((it >> 10) & 1023u); J = (int)(it & 1023u);
-        return true;
+        return b < a.B;       // the list may have been built for a larger batch: any prefix of it is balanced too
     }
     return decode_gemm_item(a, i, b, I, J);
 }
@@ -286,8 +286,10 @@ __device__ __forceinline__ bool gemm_item(const GArgs& a, int i, int& b, int& I,
 // carried 7 % (L21, T), 23 % (SYRK) and 6-38 % (LAUUM) more k blocks than the average (15 systems, n = 2048 / 4096).  Here the
 // kept tiles of each system are sorted by weight, systems stay in sequence (their digit planes share L2), and every round
 // of `grid` items is dealt heaviest-first to the CTAs with the least work so far: the loads end within ~1 % of each other.
-// Deterministic (a pure function of the shape), so results stay reproducible run to run.
-inline void make_schedule(int M, int N, int K, int B, int krange, int lower_only, int grid, std::vector<uint32_t>& out) {
+// Deterministic (a pure function of the shape), so results stay reproducible run to run.  Because the dealing is incremental,
+// every prefix of the list that ends at a round boundary is balanced as well: a list built for B systems serves any smaller
+// batch (entries of systems >= B are skipped by the kernel).  Returns the kept tiles per system.
+inline int make_schedule(int M, int N, int K, int B, int krange, int lower_only, int grid, std::vector<uint32_t>& out) {
     const int nI = M / BLK_C, nJ = N / BLK_R, nkb = K / BLK_K;
     struct It { uint32_t id; float w; };
     std::vector<It> all;
@@ -324,6 +326,7 @@ inline void make_schedule(int M, int N, int K, int B, int krange, int lower_only
             load[order[k]] += win[k].w;
         }
     }
+    return (int)(all.size() / (size_t)std::max(B, 1));
 }
 
 constexpr int GEMM_STATIC_SMEM = 6 * 1024;                   // gx_s / ga_s of the gradient epilogue + slack

@@ -53,7 +53,7 @@ int run_case(const Case& c, int n, int B, int ld, const std::vector<double>& hA,
         std::vector<uint32_t> list;
         const int items = (n / oz::BLK_C) * (n / oz::BLK_R) * B;
         const int grid = items < sm ? items : sm;
-        oz::make_schedule(n, n, n, B, c.krange, c.lower_only, grid, list);
+        oz::make_schedule(n, n, n, B + (getenv("OZ_SCHED_EXTRA") ? atoi(getenv("OZ_SCHED_EXTRA")) : 0), c.krange, c.lower_only, grid, list);
         CK(cudaMalloc(&dsched, list.size() * 4));
         CK(cudaMemcpy(dsched, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
         a.sched = dsched; a.n_sched = (int)list.size(); a.sched_grid = grid;

@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def algorithmic_bytes_per_round(N, B, s_factor=7, s_lauum=6, min_k=1024):
+def algorithmic_bytes_per_round(N, B, s_factor=7, s_lauum=6, min_k=512):
     """Digit planes read once + FP64 tiles written (read-modify-written for the SYRK) by the int8 launches of one
     evaluation round, per the recursion in exq_api.cu (factor_rec / lauum): node of half-size h --
     L21 = A21 Linv11^T, A22 -= L21 L21^T (lower), T = L21 Linv11, Linv21 = -Linv22 T -- and K^-1 = Linv^T Linv."""
