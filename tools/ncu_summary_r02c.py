@@ -90,9 +90,9 @@ def main():
     p = os.path.join(G, "launches_r02c.csv")
     if os.path.exists(p):
         shutil.copy(p, os.path.join(ROOT, "profiles", "ncu_launches_r02_final.csv"))
-        lines += ["## launch list of `bench.py --steps 1 --warmup 1 --no-cpu-baseline` (about 2.3 design batches: 1 warm-up, 1 timed, the",
-                  "extra instrumented step; `--metrics gpu__time_duration.sum`: cold-cache and serialised, so compare SHARES with the bench's",
-                  "CUDA-event times, not absolutes)", ""] + base.launch_table(p) + [""]
+        lines += ["## launch list of `bench.py --steps 1 --warmup 1 --no-cpu-baseline` (4 design batches: warm-up, timed resident, timed end-to-end,",
+                  "the extra instrumented step; `--metrics gpu__time_duration.sum`: cold-cache and serialised, so compare SHARES with the bench's",
+                  "CUDA-event times, not absolutes)", ""] + [l.replace("gemm_kernel<7,  |", "gemm_kernel<7, -1> |") for l in base.launch_table(p)] + [""]
     p = os.path.join(G, "prof_ozgemm_m_r02c.ncu-rep")
     if os.path.exists(p):
         tab, res = round_table(p)
