@@ -44,6 +44,7 @@ SIGNATURES = {
     "exq_set_grad_fused": (C.c_int, [C.c_int]),
     "exq_gp_kappa": (C.c_int, [_vp, _dp, _ip]),
     "exq_int8_gemm_ops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "exq_int8_gemm_schedule": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_int64]),
     "exq_timer_start": (C.c_int, []),
     "exq_timer_stop": (C.c_int, [_dp]),
     "exq_prof_enable": (C.c_int, [C.c_int]),
@@ -516,6 +517,19 @@ KR_FULL, KR_LE_J, KR_GE_J, KR_LE_I, KR_GE_I = range(5)
 def int8_gemm_ops(M: int, N: int, K: int, B: int, krange: int, lower_only: bool, digits: int) -> float:
     """int8 operations the factorisation GEMM kernel issues for this product (host arithmetic, no GPU needed)."""
     return float(load().exq_int8_gemm_ops(M, N, K, B, krange, int(bool(lower_only)), digits))
+
+
+def int8_gemm_schedule(M: int, N: int, K: int, B: int, krange: int, lower_only: bool, grid: int) -> np.ndarray:
+    """Balanced work list of the factorisation GEMM kernel for this product on ``grid`` CTAs (host arithmetic, no GPU
+    needed): entry i = item of CTA i % grid in round i // grid, packed (system << 20 | row tile << 10 | column tile),
+    0xffffffff = idle."""
+    lib = load()
+    n = int(lib.exq_int8_gemm_schedule(M, N, K, B, krange, int(bool(lower_only)), grid, None, 0))
+    if n < 0:
+        raise ValueError("exq_int8_gemm_schedule: bad shape")
+    out = np.empty(n, dtype=np.uint32)
+    lib.exq_int8_gemm_schedule(M, N, K, B, krange, int(bool(lower_only)), grid, out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+    return out
 
 
 def set_int8_digits(variance_digits: int, factor_digits: int) -> None:

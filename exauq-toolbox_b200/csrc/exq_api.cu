@@ -1304,6 +1304,17 @@ double exq_int8_gemm_ops(int M, int N, int K, int B, int krange, int lower_only,
     return oz::gemm_issued_ops(M, N, K, B, krange, lower_only, digits);
 }
 
+int64_t exq_int8_gemm_schedule(int M, int N, int K, int B, int krange, int lower_only, int grid, uint32_t* out, int64_t cap) {
+    if (M < 128 || N < 64 || K < 128 || (M % 128) || (N % 64) || (K % 128) || B < 1 || B > 1023 || grid < 1 || krange < 0 || krange > 4 ||
+        M / 128 > 1023 || N / 64 > 1023)
+        return -1;
+    std::vector<uint32_t> list;
+    oz::make_schedule(M, N, K, B, krange, lower_only, grid, list);
+    if (out)
+        for (int64_t i = 0; i < (int64_t)list.size() && i < cap; i++) out[i] = list[i];
+    return (int64_t)list.size();
+}
+
 int exq_timer_start(void) {
     REQUIRE_READY();
     CUDA_TRY(cudaEventRecord(g.t0, g.stream));

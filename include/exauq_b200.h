@@ -102,6 +102,11 @@ int exq_gp_kappa(exq_gp_t gp, double* kappa, int* on_fp64);
  * krange = 0 full, 1 k <= j, 2 k >= j, 3 k <= i, 4 k >= i; lower_only skips tiles above the diagonal).  Host
  * arithmetic only -- the roofline's operation count, exposed so that tests can re-derive it.  < 0: bad shape. */
 double exq_int8_gemm_ops(int M, int N, int K, int B, int krange, int lower_only, int digits);
+/* The balanced static work list oz::gemm_kernel walks for this product on `grid` CTAs (csrc/ozaki_gemm.cuh, make_schedule):
+ * entry i is the item of CTA i % grid in round i / grid, packed (system << 20 | row tile << 10 | column tile),
+ * 0xffffffff = idle.  Writes at most `cap` entries to `out` (may be NULL) and returns the length of the list, < 0 for a
+ * bad shape.  Host arithmetic only -- exposed so that tests can check coverage and balance without a GPU. */
+int64_t exq_int8_gemm_schedule(int M, int N, int K, int B, int krange, int lower_only, int grid, uint32_t* out, int64_t cap);
 
 /* CUDA-event timing on the library stream (bench.py / roofline).  exq_timer_* brackets a
  * region; exq_prof_* accumulates per-class kernel time between reset and get. */

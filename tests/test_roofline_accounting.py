@@ -108,3 +108,85 @@ def test_whole_recursion_matches_the_bench_accounting():
     # 28 (or 21) int8 products per FP64 product, times the tile overhang of the triangular ranges (< 8 %)
     assert 24.0 < ratio < 28.0 * 1.08, ratio
     assert np.isfinite(ratio)
+
+
+# ---- balanced work lists (csrc/ozaki_gemm.cuh: make_schedule) ------------------------------------------------------------
+SCHED_NONE = 0xFFFFFFFF
+
+
+def _tile_weight(M, N, K, kr, I, J):
+    """128-byte k blocks the kernel walks for output tile (I, J) -- the same widening as kblocks() above."""
+    nkb = K // BLK_K
+    rows = (I * BLK_C, I * BLK_C + BLK_C - 1)
+    cols = (J * BLK_R, J * BLK_R + BLK_R - 1)
+    lo, hi = 0, nkb
+    if kr == KR_LE_J:
+        hi = min(nkb, cols[1] // BLK_K + 1)
+    elif kr == KR_GE_J:
+        lo = cols[0] // BLK_K
+    elif kr == KR_LE_I:
+        hi = min(nkb, rows[1] // BLK_K + 1)
+    elif kr == KR_GE_I:
+        lo = rows[0] // BLK_K
+    return ((hi - 1) * BLK_K) // PIPE_K - (lo * BLK_K) // PIPE_K + 1 if hi > lo else 0
+
+
+def _loads(sched, grid, M, N, K, kr, B=None):
+    """k blocks per CTA when CTA c walks entries c, c + grid, ... (entries of systems >= B are skipped)"""
+    load = np.zeros(grid)
+    for i, it in enumerate(sched):
+        if it == SCHED_NONE:
+            continue
+        b, I, J = int(it) >> 20, (int(it) >> 10) & 1023, int(it) & 1023
+        if B is not None and b >= B:
+            continue
+        load[i % grid] += _tile_weight(M, N, K, kr, I, J)
+    return load
+
+
+@pytest.mark.parametrize("name,M,N,K,kr,lower,S", PRODUCTS)
+def test_work_list_covers_every_kept_tile_once_and_is_balanced(name, M, N, K, kr, lower, S):
+    B, grid = 15, 148
+    sched = _lib.int8_gemm_schedule(M, N, K, B, kr, bool(lower), grid)
+    assert len(sched) % grid == 0
+    items = sched[sched != SCHED_NONE]
+    want = {(b << 20) | (i << 10) | j for b in range(B) for i in range(M // BLK_C) for j in range(N // BLK_R)
+            if not (lower and j * BLK_R > i * BLK_C + BLK_C - 1)}
+    assert len(items) == len(want) and set(int(x) for x in items) == want, name
+    # the same number of k blocks as the arithmetic walk issues
+    load = _loads(sched, grid, M, N, K, kr)
+    assert load.sum() * BLK_C * BLK_R * PIPE_K * 2.0 * (S * (S + 1) // 2) == _lib.int8_gemm_ops(M, N, K, B, kr, bool(lower), S)
+    # systems stay in sequence (their digit planes share L2): per CTA the system index never decreases
+    for c in range(grid):
+        mine = sched[c::grid]
+        sysid = (mine[mine != SCHED_NONE] >> 20).astype(int)
+        assert np.all(np.diff(sysid) >= 0), name
+    # balance: the busiest CTA within one heavy tile of the average (the arithmetic walk: 7-38 % above it)
+    heaviest = max(_tile_weight(M, N, K, kr, i, j) for i in range(M // BLK_C) for j in range(N // BLK_R))
+    assert load.max() - load.mean() <= heaviest, (name, load.max(), load.mean())
+    if len(items) >= 20 * grid:
+        assert load.max() <= 1.03 * load.mean(), (name, load.max() / load.mean())
+
+
+def test_prefix_of_a_work_list_serves_a_smaller_batch():
+    """The library builds a list for the next power of two of the batch and uses the prefix of the systems it has."""
+    M = N = K = 2048
+    grid = 148
+    for kr, lower in ((KR_LE_J, 0), (KR_FULL, 1), (KR_GE_I, 1)):
+        full = _lib.int8_gemm_schedule(M, N, K, 16, kr, bool(lower), grid)
+        kept = int(np.count_nonzero(full != SCHED_NONE)) // 16
+        for B in (9, 13, 15):
+            n = -(-B * kept // grid) * grid                      # rounds that hold the first B systems
+            prefix = full[:n]
+            got = prefix[(prefix != SCHED_NONE) & ((prefix >> 20) < B)]
+            own = _lib.int8_gemm_schedule(M, N, K, B, kr, bool(lower), grid)
+            assert set(int(x) for x in got) == set(int(x) for x in own[own != SCHED_NONE])
+            load = _loads(prefix, grid, M, N, K, kr, B)
+            assert load.max() <= 1.05 * load.mean(), (kr, B, load.max() / load.mean())
+
+
+def test_work_list_refuses_bad_shapes():
+    with pytest.raises(ValueError):
+        _lib.int8_gemm_schedule(100, 64, 128, 1, 0, False, 148)
+    with pytest.raises(ValueError):
+        _lib.int8_gemm_schedule(128, 64, 64, 1, 0, False, 148)     # k blocks are 128 bytes
