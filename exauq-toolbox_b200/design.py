@@ -327,27 +327,60 @@ def design_batch(
     return pts, gidx, vals, theta
 
 
+def _polish_batched(neg_pei, x0: np.ndarray, f0: float, bounds):
+    """The polish step of scipy's differential evolution -- L-BFGS-B from the best population member with the
+    2-point finite-difference gradient scipy's ``minimize`` builds when no ``jac`` is given
+    (h_k = sqrt(eps) * sign(x_k) * max(1, |x_k|), flipped at a bound) -- but with the d + 1 points of every gradient
+    evaluated in ONE device call instead of d + 1 scalar calls (device-side polish).
+    Returns (x, f) of the polished point when it improves on (x0, f0) and respects the bounds, else (x0, f0) --
+    the acceptance rule of ``DifferentialEvolutionSolver.solve``."""
+    import scipy.optimize
+
+    lb = np.array([b[0] for b in bounds], dtype=float)
+    ub = np.array([b[1] for b in bounds], dtype=float)
+    d = x0.shape[0]
+    root_eps = np.sqrt(np.finfo(float).eps)
+
+    def fun_and_grad(x):
+        x = np.asarray(x, dtype=float)
+        h = root_eps * np.where(x >= 0, 1.0, -1.0) * np.maximum(1.0, np.abs(x))
+        flip = (x + h > ub) | (x + h < lb)
+        h = np.where(flip, -h, h)
+        pts = np.tile(x, (d + 1, 1))
+        pts[1:] += np.diag(h)
+        dx = pts[1:, :][np.arange(d), np.arange(d)] - x          # the step actually representable
+        vals = np.asarray(neg_pei(pts.T), dtype=float)
+        return float(vals[0]), (vals[1:] - vals[0]) / dx
+
+    res = scipy.optimize.minimize(fun_and_grad, x0, jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)))
+    if res.fun < f0 and np.all(res.x <= ub) and np.all(res.x >= lb):
+        return np.array(res.x, dtype=float), float(res.fun)
+    return x0, f0
+
+
 def maximise_pei_de(gp_e, bounds: Sequence[Sequence[float]], repulsion_points, max_target: float,
-                    seed: Optional[int] = None, cand_factory=DeviceCandidates, popsize: int = 15, **de_kwargs):
+                    seed: Optional[int] = None, cand_factory=DeviceCandidates, popsize: int = 15, polish: bool = True,
+                    **de_kwargs):
     """Continuous maximisation of the pseudo-expected improvement of a fitted errors GP over the
     domain box, with the optimiser the reference uses -- scipy ``differential_evolution`` with
     ``tol = atol = 1e-9`` (exauq/utilities/optimisation.py:14-104) -- but with every generation's
     population evaluated in ONE device call (``vectorized=True``, ``updating='deferred'``; the
-    reference's default immediate updating is inherently one point at a time).  Returns
-    ``(x, pei(x))`` like ``maximise``.  SURVEY.md section 8f item 1."""
+    reference's default immediate updating is inherently one point at a time) and the final polish
+    (L-BFGS-B from the best member, scipy's default) with batched finite-difference gradients
+    (``_polish_batched``).  Returns ``(x, pei(x))`` like ``maximise``.  SURVEY.md section 8f item 1."""
     import scipy.optimize
 
     d = len(bounds)
     rep = np.asarray(repulsion_points, dtype=float).reshape(-1, d) if len(repulsion_points) else None
-    state = {"cand": None}
+    state: dict = {}
 
     def neg_pei(x):
         pts = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=float).T))     # (S, d)
         if pts.shape[1] != d:
             pts = pts.reshape(-1, d)
-        c = state["cand"]
-        if c is None or c.M != pts.shape[0]:
-            c = state["cand"] = cand_factory(pts)
+        c = state.get(pts.shape[0])                # one resident candidate set per population size (DE / polish)
+        if c is None:
+            c = state[pts.shape[0]] = cand_factory(pts)
         else:
             c.set_points(pts)
         c.pei_eval(gp_e, rep, max_target)
@@ -356,10 +389,13 @@ def maximise_pei_de(gp_e, bounds: Sequence[Sequence[float]], repulsion_points, m
 
     result = scipy.optimize.differential_evolution(neg_pei, bounds=[tuple(b) for b in bounds], tol=1e-9, atol=1e-9,
                                                    seed=seed, vectorized=True, updating="deferred", popsize=popsize,
-                                                   **de_kwargs)
+                                                   polish=False, **de_kwargs)
     if not result.success:
         raise RuntimeError(f"Maximisation failed to converge: {result.message}")
-    return np.array(result.x, dtype=float), -float(result.fun)
+    x, f = np.array(result.x, dtype=float), float(result.fun)
+    if polish:
+        x, f = _polish_batched(neg_pei, x, f, bounds)
+    return x, -f
 
 
 def multi_level_loo_errors(levels: dict, coefficients: dict, gp_factory=DeviceGP):

@@ -231,6 +231,40 @@ def test_vectorised_de_maximiser_finds_the_reference_maximum():
     assert np.allclose(x, np.array(x_ref), atol=1e-4)
 
 
+def test_batched_polish_equals_scipys_scalar_polish():
+    """design._polish_batched: the L-BFGS-B polish of scipy's differential evolution with the d + 1 points of each
+    finite-difference gradient in ONE objective call -- same iterates as scipy's own scalar 2-point scheme, incl. at a bound."""
+    from scipy.optimize import minimize
+
+    from exauq_toolbox_b200.design import _polish_batched
+
+    c = np.array([0.3, 2.5, 0.55])            # the second coordinate's optimum lies beyond the upper bound
+    calls = []
+
+    def f_scalar(x):
+        x = np.asarray(x, dtype=float)
+        return float(np.sum((x - c) ** 4) + 0.1 * np.sum(np.cos(5 * x)) + 0.05 * x[0] * x[2])
+
+    def f_batched(xt):                        # (d, S) like a vectorised DE objective
+        pts = np.asarray(xt, dtype=float).T
+        calls.append(pts.shape[0])
+        return np.array([f_scalar(p) for p in pts])
+
+    bounds = [(0.0, 1.0)] * 3
+    x0 = np.array([0.9, 0.8, 0.1])
+    ref = minimize(f_scalar, x0, method="L-BFGS-B", bounds=bounds)
+    x, fx = _polish_batched(f_batched, x0, f_scalar(x0), bounds)
+    assert set(calls) == {4}                  # every objective call carries the point and its d neighbours
+    assert len(calls) <= ref.nfev // 4 + 1    # scipy counts each of the d + 1 scalar evaluations
+    assert np.allclose(x, ref.x, atol=1e-7) and abs(fx - ref.fun) <= 1e-12 * max(1.0, abs(ref.fun))
+    assert x[1] == 1.0                        # stays on the bound
+    # never worse than the start, and a start that is given a better value than it has is returned unchanged
+    x2, f2 = _polish_batched(f_batched, x, fx, bounds)
+    assert f2 <= fx and np.allclose(x2, x, atol=1e-4)
+    x3, f3 = _polish_batched(f_batched, x, -1e9, bounds)
+    assert np.array_equal(x3, x) and f3 == -1e9
+
+
 def test_lockstep_lbfgsb_stepper_reproduces_scipy_minimize():
     """_LbfgsbStepper drives scipy's own L-BFGS-B core: iterates, optimum and evaluation count equal
     scipy.optimize.minimize(method='L-BFGS-B') bit for bit, with and without bounds."""
