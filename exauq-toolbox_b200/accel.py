@@ -103,19 +103,76 @@ def batched_maximise(func, domain, seed: Optional[int] = None, _fallback=None):
     return Input(*x), float(val)
 
 
+def _coords(x, dim: int):
+    """Coordinates of an ``Input`` as a float array of length ``dim``, or None when that is not what it is."""
+    if not isinstance(x, Input) or len(x) != dim or dim == 0:
+        return None
+    try:
+        v = np.asarray(x.value, dtype=float).reshape(-1)
+    except (TypeError, ValueError):
+        return None
+    return v if v.shape[0] == dim and np.all(np.isfinite(v)) else None
+
+
+def add_repulsion_points_vectorised(pei, repulsion_points, _fallback=None) -> None:
+    """``PEICalculator._add_repulsion_points`` (exauq/core/designers.py:601-608) without its O(P * N) Python loop.
+
+    The reference appends every new point that is not ``==`` to a current repulsion point -- the other repulsion points
+    followed by the training inputs, rebuilt as a tuple and scanned with ``Input.__eq__`` for every new point: 1.2
+    million tolerance comparisons for the 272 pseudopoints of an N = 4096, d = 8 design batch, 3.5 of the 5.5 s the
+    unchanged ``compute_single_level_loo_samples`` took.  ``Input.__eq__`` is ``math.isclose`` per coordinate with
+    ``rel_tol = abs_tol = exauq.core.numerics.FLOAT_TOLERANCE`` (modelling.py:287-309, numerics.py:31-73); the same
+    rule is applied here to whole arrays, new points taken in order so that duplicates among them are dropped as the
+    reference drops them.  Anything that is not a finite ``Input`` of the domain's dimension goes to the reference."""
+    import exauq.core.numerics as numerics
+
+    if _fallback is None:
+        from exauq.core.designers import PEICalculator
+        _fallback = PEICalculator._add_repulsion_points
+    new = list(repulsion_points)
+    if not new:
+        return None
+    dim = pei._domain.dim
+    current = list(pei._other_repulsion_points) + [datum.input for datum in pei._gp.training_data]
+    rows = [_coords(x, dim) for x in current]
+    cand = [_coords(x, dim) for x in new]
+    if any(r is None for r in rows) or any(c is None for c in cand):
+        return _fallback(pei, new)
+    tol = numerics.FLOAT_TOLERANCE or 1e-9                   # equal_within_tolerance: `rel_tol or FLOAT_TOLERANCE`
+    E = np.empty((len(rows) + len(cand), dim))
+    if rows:
+        E[: len(rows)] = np.array(rows)
+    n = len(rows)
+    for x, c in zip(new, cand):
+        A = E[:n]
+        close = np.abs(A - c) <= np.maximum(tol * np.maximum(np.abs(A), np.abs(c)), tol)     # math.isclose
+        if not bool(np.any(np.all(close, axis=1))):
+            pei._other_repulsion_points.append(x)
+            E[n] = c
+            n += 1
+    return None
+
+
 @contextlib.contextmanager
 def accelerate_designers():
     """Inside the ``with`` block ``exauq.core.designers`` maximises pseudo-expected improvements of B200 GPs through
-    ``batched_maximise``; every other call behaves as before.  The module attribute is restored on exit."""
+    ``batched_maximise`` and ``PEICalculator`` collects its repulsion points through
+    ``add_repulsion_points_vectorised``; every other call behaves as before.  Both are restored on exit."""
     import exauq.core.designers as designers
 
     original = designers.maximise
+    original_add = designers.PEICalculator._add_repulsion_points
 
     def patched(func, domain, seed=None):
         return batched_maximise(func, domain, seed=seed, _fallback=original)
 
+    def patched_add(self, repulsion_points):
+        return add_repulsion_points_vectorised(self, repulsion_points, _fallback=original_add)
+
     designers.maximise = patched
+    designers.PEICalculator._add_repulsion_points = patched_add
     try:
         yield
     finally:
         designers.maximise = original
+        designers.PEICalculator._add_repulsion_points = original_add

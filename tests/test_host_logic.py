@@ -231,6 +231,41 @@ def test_vectorised_de_maximiser_finds_the_reference_maximum():
     assert np.allclose(x, np.array(x_ref), atol=1e-4)
 
 
+@needs_exauq
+def test_vectorised_repulsion_point_collection_equals_the_reference_loop():
+    """accel.add_repulsion_points_vectorised (patched in by accelerate_designers) keeps exactly the points, in the order,
+    that PEICalculator._add_repulsion_points keeps (exauq/core/designers.py:601-608): pseudopoints at construction,
+    then points equal within tolerance to a training input / an earlier point / each other, and new ones."""
+    from exauq.core.designers import PEICalculator
+    from exauq.core.emulators import MogpEmulator, MogpHyperparameters
+    from exauq.core.modelling import Input, SimulatorDomain, TrainingDatum
+
+    from exauq_toolbox_b200.accel import accelerate_designers
+
+    g = load_golden("fixed_matern_d3_n40.json")
+    X, y = np.array(g["X"]), np.array(g["y"])
+    X[3] = [0.0, 1.0, 0.5]                                    # a training input on an edge: its pseudopoints coincide
+    X[7] = [1.0, 1.0, 1.0]                                    # ... and one in a corner
+    bounds = [(0.0, 1.0)] * 3
+    ref = MogpEmulator(kernel="Matern52")
+    ref.fit([TrainingDatum(Input(*x), float(t)) for x, t in zip(X, y)], hyperparameters=MogpHyperparameters([0.4] * 3, 1.3, 0.0))
+    domain = SimulatorDomain(bounds)
+    extra = [Input(0.2, 0.3, 0.4), Input(*X[5]), Input(*(X[6] + 5e-10)), Input(0.2 + 1e-12, 0.3, 0.4), Input(0.9, 0.1, 0.5),
+             Input(0.9, 0.1, 0.5)]
+    stock = PEICalculator(domain, ref, additional_repulsion_pts=extra[:2])
+    stock.add_repulsion_points(extra[2:])
+    with accelerate_designers():
+        fast = PEICalculator(domain, ref, additional_repulsion_pts=extra[:2])
+        fast.add_repulsion_points(extra[2:])
+    a, b = stock._other_repulsion_points, fast._other_repulsion_points
+    assert len(a) == len(b) and all(p is q or tuple(p.value) == tuple(q.value) for p, q in zip(a, b))
+    assert Input(0.2, 0.3, 0.4) in b and sum(1 for p in b if p == Input(0.9, 0.1, 0.5)) == 1
+    assert all(not (p == Input(*X[5])) for p in b)             # a training input is never an "other" repulsion point
+    # restored on exit
+    import exauq.core.designers as designers
+    assert designers.PEICalculator._add_repulsion_points.__name__ == "_add_repulsion_points"
+
+
 def test_batched_polish_equals_scipys_scalar_polish():
     """design._polish_batched: the L-BFGS-B polish of scipy's differential evolution with the d + 1 points of each
     finite-difference gradient in ONE objective call -- same iterates as scipy's own scalar 2-point scheme, incl. at a bound."""

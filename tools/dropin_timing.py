@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--stock-batch", type=int, default=0, help="design points through the stock scalar path (0: skip)")
+    ap.add_argument("--profile", action="store_true", help="cProfile of the fast path (top 30 by cumulative time on stderr)")
     a = ap.parse_args()
     import exauq.core.designers as designers
     from exauq.core.modelling import GaussianProcessHyperparameters, Input, SimulatorDomain, TrainingDatum
@@ -51,8 +52,17 @@ def main():
     np.random.seed(5)
     l0 = _lib.launch_count()
     t0 = time.perf_counter()
+    prof = None
+    if a.profile:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     with accelerate_designers():
         pts = designers.compute_single_level_loo_samples(gp, fast, batch_size=a.batch, seed=11)
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
     out["fast"] = {"compute_single_level_loo_samples_s": time.perf_counter() - t0,
                    "gpu_launches": _lib.launch_count() - l0,
                    "points": [[float(c) for c in p] for p in pts]}
