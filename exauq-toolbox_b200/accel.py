@@ -153,15 +153,98 @@ def add_repulsion_points_vectorised(pei, repulsion_points, _fallback=None) -> No
     return None
 
 
+def find_input_repetition_across_levels(training_data, _fallback=None):
+    """``exauq.core.designers._find_input_repetition_across_levels`` (designers.py:925-955) without the product over all
+    levels' inputs (4096 x 1024 x 256 tuples at BASELINE.json's multi-level size: the reference cannot finish it).
+
+    Returns what the reference returns: ``None`` with fewer than two levels or no input shared by two levels, else
+    ``(x1, level1, level2)`` for the FIRST equal pair its enumeration meets -- ``itertools.product`` over the levels in
+    mapping order (first level slowest), ``itertools.combinations`` inside each tuple.  A tuple that contains the equal
+    pair (level a, index i) / (level b, index j) is componentwise >= the tuple with i at a, j at b and zeros elsewhere, so
+    the first tuple with any equal pair is the lexicographic minimum of those; inside it the first combination that is an
+    equal pair wins.  Equality is ``Input.__eq__``: ``math.isclose`` per coordinate with the toolbox tolerance."""
+    import exauq.core.numerics as numerics
+
+    if _fallback is None:
+        from exauq.core.designers import _find_input_repetition_across_levels as _fallback
+    levels = list(training_data.keys())
+    if len(levels) < 2:
+        return None
+    # compute_multi_level_loo_prediction repeats this check for every left-out index (designers.py:894) on the same
+    # tuples of training data: the answer for the same objects under the same tolerance is remembered
+    data = [training_data[lv] for lv in levels]
+    key = (tuple(levels), tuple(id(t) for t in data), tuple(len(t) for t in data), numerics.FLOAT_TOLERANCE)
+    if _REPETITION_CACHE.get("key") == key and all(isinstance(t, tuple) for t in data):
+        return _REPETITION_CACHE["value"]
+    result = _find_repetition(levels, data, training_data, _fallback)
+    if all(isinstance(t, tuple) for t in data):
+        _REPETITION_CACHE.update(key=key, value=result, keep=data)     # `keep` pins the objects the ids belong to
+    return result
+
+
+_REPETITION_CACHE: dict = {}
+
+
+def _find_repetition(levels, data, training_data, _fallback):
+    import exauq.core.numerics as numerics
+
+    inputs = [[datum.input for datum in t] for t in data]
+    if any(len(x) == 0 for x in inputs):
+        return None                                           # an empty factor: the product has no tuples
+    dim = len(inputs[0][0])
+    coords = [[_coords(x, dim) for x in xs] for xs in inputs]
+    if any(c is None for cs in coords for c in cs):
+        return _fallback(training_data)
+    tol = numerics.FLOAT_TOLERANCE or 1e-9
+    X = np.array([c for cs in coords for c in cs])
+    pos = np.concatenate([np.full(len(cs), a) for a, cs in enumerate(coords)])
+    idx = np.concatenate([np.arange(len(cs)) for cs in coords])
+    order = np.argsort(X[:, 0], kind="stable")
+    x0 = X[order, 0]
+    hi = np.searchsorted(x0, x0 + 2.1 * tol * np.maximum(1.0, np.abs(x0)), side="right")
+    pairs = []                                                # (a, i, b, j) with a < b
+    for s_ in range(X.shape[0]):
+        if hi[s_] <= s_ + 1:
+            continue
+        p = order[s_]
+        nb = order[s_ + 1 : hi[s_]]
+        nb = nb[pos[nb] != pos[p]]
+        if nb.size == 0:
+            continue
+        A, c = X[nb], X[p]
+        close = np.all(np.abs(A - c) <= np.maximum(tol * np.maximum(np.abs(A), np.abs(c)), tol), axis=1)
+        for q in nb[close]:
+            (a, i), (b, j) = sorted([(int(pos[p]), int(idx[p])), (int(pos[q]), int(idx[q]))])
+            pairs.append((a, i, b, j))
+    if not pairs:
+        return None
+    L = len(levels)
+
+    def first_tuple(pr):
+        v = [0] * L
+        v[pr[0]], v[pr[2]] = pr[1], pr[3]
+        return tuple(v)
+
+    v = min(first_tuple(pr) for pr in pairs)
+    # every equal pair inside that tuple, first in itertools.combinations order
+    inside = sorted((a, b) for (a, i, b, j) in pairs if v[a] == i and v[b] == j)
+    # index-0 members of the other levels may be equal to each other too without being in `pairs` order: they are in
+    # `pairs` (all cross-level equal pairs were collected), so `inside` is complete
+    a, b = inside[0]
+    return inputs[a][v[a]], levels[a], levels[b]
+
+
 @contextlib.contextmanager
 def accelerate_designers():
     """Inside the ``with`` block ``exauq.core.designers`` maximises pseudo-expected improvements of B200 GPs through
-    ``batched_maximise`` and ``PEICalculator`` collects its repulsion points through
-    ``add_repulsion_points_vectorised``; every other call behaves as before.  Both are restored on exit."""
+    ``batched_maximise``, ``PEICalculator`` collects its repulsion points through ``add_repulsion_points_vectorised`` and
+    the cross-level repetition check of the multi-level designers runs as ``find_input_repetition_across_levels``; every
+    other call behaves as before.  All three are restored on exit."""
     import exauq.core.designers as designers
 
     original = designers.maximise
     original_add = designers.PEICalculator._add_repulsion_points
+    original_rep = designers._find_input_repetition_across_levels
 
     def patched(func, domain, seed=None):
         return batched_maximise(func, domain, seed=seed, _fallback=original)
@@ -169,10 +252,15 @@ def accelerate_designers():
     def patched_add(self, repulsion_points):
         return add_repulsion_points_vectorised(self, repulsion_points, _fallback=original_add)
 
+    def patched_rep(training_data):
+        return find_input_repetition_across_levels(training_data, _fallback=original_rep)
+
     designers.maximise = patched
     designers.PEICalculator._add_repulsion_points = patched_add
+    designers._find_input_repetition_across_levels = patched_rep
     try:
         yield
     finally:
         designers.maximise = original
         designers.PEICalculator._add_repulsion_points = original_add
+        designers._find_input_repetition_across_levels = original_rep

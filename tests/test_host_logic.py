@@ -266,6 +266,40 @@ def test_vectorised_repulsion_point_collection_equals_the_reference_loop():
     assert designers.PEICalculator._add_repulsion_points.__name__ == "_add_repulsion_points"
 
 
+@needs_exauq
+def test_cross_level_repetition_check_returns_what_the_reference_returns():
+    """accel.find_input_repetition_across_levels against exauq.core.designers._find_input_repetition_across_levels
+    (designers.py:925-955): the same (input object, level, level) -- the FIRST equal pair of the reference's
+    product / combinations enumeration -- over random multi-level data with planted repetitions (exact, within
+    tolerance, several at once, between any two levels)."""
+    from exauq.core.designers import _find_input_repetition_across_levels as reference
+    from exauq.core.modelling import Input, MultiLevel, TrainingDatum
+
+    from exauq_toolbox_b200.accel import find_input_repetition_across_levels as fast
+
+    rng = np.random.default_rng(11)
+    n_hits = 0
+    for trial in range(120):
+        n_levels = int(rng.integers(1, 4))
+        sizes = [int(rng.integers(1, 6)) for _ in range(n_levels)]
+        level_ids = list(rng.permutation([1, 2, 3, 5])[:n_levels])
+        pts = [rng.uniform(0, 1, (n, 2)) for n in sizes]
+        for _ in range(int(rng.integers(0, 3))):                # plant up to two repetitions
+            if n_levels < 2:
+                break
+            a, b = rng.choice(n_levels, 2, replace=False)
+            pts[b][rng.integers(sizes[b])] = pts[a][rng.integers(sizes[a])] + rng.choice([0.0, 4e-10, -4e-10, 5e-9])
+        data = MultiLevel({int(lv): tuple(TrainingDatum(Input(*x), 1.0) for x in p) for lv, p in zip(level_ids, pts)})
+        want, got = reference(data), fast(data)
+        assert (want is None) == (got is None), trial
+        if want is not None:
+            n_hits += 1
+            assert got[0] is want[0] and got[1:] == want[1:], (trial, want, got)
+        assert fast(data) is got or fast(data) == got          # remembered answer for the same tuples
+    assert n_hits >= 30
+    assert fast(MultiLevel({1: (TrainingDatum(Input(0.5), 1.0),), 2: ()})) is None
+
+
 def test_batched_polish_equals_scipys_scalar_polish():
     """design._polish_batched: the L-BFGS-B polish of scipy's differential evolution with the d + 1 points of each
     finite-difference gradient in ONE objective call -- same iterates as scipy's own scalar 2-point scheme, incl. at a bound."""
