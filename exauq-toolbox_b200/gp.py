@@ -104,6 +104,7 @@ class _FitState:
         self.ids = np.fromiter(map(id, training_data), dtype=np.int64, count=len(training_data))
         self._loo = None
         self._kinv = None
+        self._kinv_y = None
         self._lock = threading.Lock()
 
     def loo(self):
@@ -123,6 +124,17 @@ class _FitState:
                         "Cannot compute covariance inverse: Covariance Matrix is, or too close to singular."
                     ) from None
             return self._kinv
+
+
+    def kinv_y(self) -> np.ndarray:
+        """``kinv @ y`` as a column, formed once: the weights of the zero-mean prediction
+        ``covariance_matrix([x]) @ kinv @ y`` (exauq/core/designers.py:1029) that the multi-level designers evaluate for
+        every left-out input of every other level."""
+        kinv = self.kinv()
+        with self._lock:
+            if self._kinv_y is None:
+                self._kinv_y = kinv @ self.y.reshape(-1, 1)
+            return self._kinv_y
 
 
 class _LooView:

@@ -156,6 +156,55 @@ def test_multi_level_gp_and_loo(api):
         assert close(a.estimate, b.estimate, rel=1e-7, abs_=1e-8) and close(a.variance, b.variance, rel=1e-7)
 
 
+def test_accelerated_multi_level_loo_error_data_equals_the_unchanged_path(api):
+    """Inside accelerate_designers() the reference's compute_multi_level_loo_error_data (designers.py:1045-1105) --
+    zero-mean predictions through ``kinv @ y`` formed once, cross-level repetition check by a sort -- returns the
+    errors of the untouched code path on the same B200 GPs, and both agree with reference GPs."""
+    from exauq_toolbox_b200.accel import accelerate_designers, zero_mean_prediction
+
+    rng = np.random.default_rng(8)
+    d = 3
+    sizes = (40, 17, 9)
+    data = api.MultiLevel([[api.TrainingDatum(api.Input(*x), float(np.sin(3 * x[0]) + x[1] * x[2] / (lv + 1)))
+                            for x in rng.uniform(0, 1, (n, d))] for lv, n in enumerate(sizes)])
+    hps = {1: ([0.5, 0.6, 0.7], 2.0, 0.0), 2: ([0.3, 0.3, 0.4], 1.5, 0.0), 3: ([0.6, 0.2, 0.5], 0.7, 0.0)}
+    ours = api.MultiLevelGaussianProcess([api.B200GaussianProcess(kernel="Matern52") for _ in range(3)])
+    refs = api.MultiLevelGaussianProcess([api.MogpEmulator(kernel="Matern52") for _ in range(3)])
+    ours.fit(data, hyperparameters=api.MultiLevel({k: api.GaussianProcessHyperparameters(*v) for k, v in hps.items()}))
+    refs.fit(data, hyperparameters=api.MultiLevel({k: api.MogpHyperparameters(*v) for k, v in hps.items()}))
+    plain = api.designers.compute_multi_level_loo_error_data(ours)
+    with accelerate_designers():
+        fast = api.designers.compute_multi_level_loo_error_data(ours)
+    want = api.designers.compute_multi_level_loo_error_data(refs)
+    for lv in plain.levels:
+        a = np.array([t.output for t in plain[lv]])
+        b = np.array([t.output for t in fast[lv]])
+        c = np.array([t.output for t in want[lv]])
+        assert all(p.input == q.input for p, q in zip(plain[lv], fast[lv]))
+        assert close(a, b, rel=1e-10, abs_=1e-12) and close(b, c, rel=1e-6, abs_=1e-8)
+    # the patched function alone, and its error wrapping for an unfitted GP
+    x = api.Input(0.3, 0.4, 0.5)
+    p, q = zero_mean_prediction(ours[1], x), api.designers.compute_zero_mean_prediction(ours[1], x)
+    assert close(p.estimate, q.estimate, rel=1e-11, abs_=1e-13) and p.variance == q.variance
+    with pytest.raises(ValueError, match="hasn't been trained on any data"):
+        zero_mean_prediction(api.B200GaussianProcess(kernel="Matern52"), x)
+    # a repeated input across levels is reported as the reference reports it
+    bad = api.MultiLevel({1: data[1], 2: tuple(data[2]) + (api.TrainingDatum(data[1][4].input, 0.0),), 3: data[3]})
+    ours2 = api.MultiLevelGaussianProcess([api.B200GaussianProcess(kernel="Matern52") for _ in range(3)])
+    ours2.fit(bad, hyperparameters=api.MultiLevel({k: api.GaussianProcessHyperparameters(*v) for k, v in hps.items()}))
+    msgs = []
+    for ctx in (None, accelerate_designers()):
+        try:
+            if ctx is None:
+                api.designers.compute_multi_level_loo_prediction(ours2, 1, 0)
+            else:
+                with ctx:
+                    api.designers.compute_multi_level_loo_prediction(ours2, 1, 0)
+        except ValueError as e:
+            msgs.append(str(e))
+    assert len(msgs) == 2 and msgs[0] == msgs[1] and "levels 1, 2" in msgs[0]
+
+
 def test_pei_candidates_matches_reference_peicalculator(api):
     """B200GaussianProcess.pei_candidates vs the reference's PEICalculator evaluated point
     by point, including the batch loop's repulsion updates."""

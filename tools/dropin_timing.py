@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--stock-batch", type=int, default=0, help="design points through the stock scalar path (0: skip)")
     ap.add_argument("--profile", action="store_true", help="cProfile of the fast path (top 30 by cumulative time on stderr)")
+    ap.add_argument("--multi-level", default="", help="sizes 'n1,n2,n3': time the unchanged compute_multi_level_loo_samples "
+                    "(d = --d, costs 1 / 10 / 100, batch --batch) on B200 GPs inside accelerate_designers() instead")
     a = ap.parse_args()
     import exauq.core.designers as designers
     from exauq.core.modelling import GaussianProcessHyperparameters, Input, SimulatorDomain, TrainingDatum
@@ -36,6 +38,8 @@ def main():
     from exauq_toolbox_b200.workload import synthetic_problem
 
     _lib.init(0)
+    if a.multi_level:
+        return multi_level(a)
     X, y = synthetic_problem(a.n, a.d)
     t0 = time.perf_counter()
     data = [TrainingDatum(Input(*row), float(v)) for row, v in zip(X, y)]
@@ -89,6 +93,49 @@ def main():
                                   "note": "FastSimulatorDomain but the reference's scalar maximise (one predict + one "
                                           "covariance_matrix device round trip per objective evaluation)",
                                   "points": [[float(c) for c in p] for p in pts_s]}
+    print(json.dumps(out))
+
+
+def multi_level(a):
+    """BASELINE.json configs[3] through the reference's own compute_multi_level_loo_samples (designers.py:1184-1378)."""
+    import exauq.core.designers as designers
+    from exauq.core.modelling import (GaussianProcessHyperparameters, Input, MultiLevel, MultiLevelGaussianProcess,
+                                      TrainingDatum)
+
+    from exauq_toolbox_b200.accel import FastSimulatorDomain, accelerate_designers
+    from exauq_toolbox_b200.gp import B200GaussianProcess
+    from exauq_toolbox_b200.workload import synthetic_problem
+
+    sizes = [int(v) for v in a.multi_level.split(",")]
+    bounds = [(0.0, 1.0)] * a.d
+    data, hps = {}, {}
+    for lv, n in enumerate(sizes, start=1):
+        X, y = synthetic_problem(n, a.d, seed=lv)
+        data[lv] = [TrainingDatum(Input(*row), float(v) / lv) for row, v in zip(X, y)]
+        hps[lv] = GaussianProcessHyperparameters([0.5] * a.d, 1.7 / lv, 0.0)
+    mlgp = MultiLevelGaussianProcess([B200GaussianProcess(kernel="Matern52") for _ in sizes])
+    t0 = time.perf_counter()
+    mlgp.fit(MultiLevel(data), hyperparameters=MultiLevel(hps))
+    out = {"sizes": sizes, "d": a.d, "batch_size": a.batch, "fit_with_hyperparameters_s": time.perf_counter() - t0}
+    costs = MultiLevel([10.0 ** k for k in range(len(sizes))])
+    domain = FastSimulatorDomain(bounds)
+    np.random.seed(5)
+    prof = None
+    if a.profile:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
+    t0 = time.perf_counter()
+    with accelerate_designers():
+        pts = designers.compute_multi_level_loo_samples(mlgp, domain, costs, batch_size=a.batch,
+                                                        seeds=MultiLevel([11 + k for k in range(len(sizes))]))
+    out["compute_multi_level_loo_samples_s"] = time.perf_counter() - t0
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
+    out["level_chosen"] = [int(lv) for lv in pts.levels if len(pts[lv])]
+    out["points"] = {int(lv): [[float(c) for c in p] for p in pts[lv]] for lv in pts.levels}
     print(json.dumps(out))
 
 
