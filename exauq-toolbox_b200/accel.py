@@ -153,6 +153,50 @@ def add_repulsion_points_vectorised(pei, repulsion_points, _fallback=None) -> No
     return None
 
 
+def loo_errors_gp(gp, domain, loo_errors_gp=None, _fallback=None):
+    """``exauq.core.designers.compute_loo_errors_gp`` (designers.py:186-272) for a ``B200GaussianProcess``: same checks,
+    same errors, same errors-GP fit, but the N leave-one-out predictions are taken from ONE ``gp.loo_predictions()``
+    call -- the sweep the reference's loop is served from anyway, one ``fit`` + ``predict`` round trip per left-out point
+    (0.15 ms of Python each: a third of the drop-in batch at N = 4096).  The normalised expected squared error is the
+    reference's own ``GaussianProcessPrediction.nes_error``.  Anything else goes to the reference."""
+    import copy
+
+    import exauq.core.designers as designers
+    import exauq.core.numerics as numerics
+    from exauq.core.modelling import AbstractGaussianProcess, GaussianProcessPrediction, TrainingDatum
+
+    if _fallback is None:
+        _fallback = designers.compute_loo_errors_gp
+    if not (isinstance(gp, B200GaussianProcess) and isinstance(domain, SimulatorDomain)
+            and (loo_errors_gp is None or isinstance(loo_errors_gp, AbstractGaussianProcess))
+            and len(gp.training_data) >= 2):
+        return _fallback(gp, domain, loo_errors_gp)
+    state = gp._real_state()
+    X = state.X
+    # SimulatorDomain.__contains__ (modelling.py:2011-2023): the right dimension and every coordinate inside its bounds or
+    # within tolerance (math.isclose, rel = abs = FLOAT_TOLERANCE) of one
+    tol = numerics.FLOAT_TOLERANCE or 1e-9
+    lb = np.array([b[0] for b in domain.bounds], dtype=float)
+    ub = np.array([b[1] for b in domain.bounds], dtype=float)
+    inside = X.shape[1] == domain.dim
+    if inside:
+        near = lambda a, b: np.abs(a - b) <= np.maximum(tol * np.maximum(np.abs(a), np.abs(b)), tol)  # noqa: E731
+        inside = bool(np.all((near(lb, X) | (lb < X)) & (near(ub, X) | (X < ub))))
+    if not inside:
+        raise ValueError(
+            "Expected all training inputs in 'gp' to belong to the domain 'domain', but "
+            "this is not the case."
+        )
+    mean, var, _ = gp.loo_predictions()
+    error_training_data = [
+        TrainingDatum(datum.input, GaussianProcessPrediction(float(m), float(v)).nes_error(datum.output))
+        for datum, m, v in zip(gp.training_data, mean, var)
+    ]
+    gp_e = loo_errors_gp if loo_errors_gp is not None else copy.deepcopy(gp)
+    gp_e.fit(error_training_data, hyperparameter_bounds=designers._compute_loo_error_bounds(domain))
+    return gp_e
+
+
 def zero_mean_prediction(gp, x, _fallback=None):
     """``exauq.core.designers.compute_zero_mean_prediction`` (designers.py:1001-1042) for a ``B200GaussianProcess``:
     the same mean ``covariance_matrix([x]) @ kinv @ y`` with ``kinv @ y`` formed once per fit instead of an N x N
@@ -259,14 +303,15 @@ def accelerate_designers():
     """Inside the ``with`` block ``exauq.core.designers`` maximises pseudo-expected improvements of B200 GPs through
     ``batched_maximise``, ``PEICalculator`` collects its repulsion points through ``add_repulsion_points_vectorised`` and
     the cross-level repetition check and the zero-mean predictions of the multi-level designers run as
-    ``find_input_repetition_across_levels`` / ``zero_mean_prediction``; every other call behaves as before.  All four are
-    restored on exit."""
+    ``find_input_repetition_across_levels`` / ``zero_mean_prediction``, and the leave-one-out errors of a B200 GP come
+    from one sweep (``loo_errors_gp``); every other call behaves as before.  All five are restored on exit."""
     import exauq.core.designers as designers
 
     original = designers.maximise
     original_add = designers.PEICalculator._add_repulsion_points
     original_rep = designers._find_input_repetition_across_levels
     original_zmp = designers.compute_zero_mean_prediction
+    original_loo = designers.compute_loo_errors_gp
 
     def patched(func, domain, seed=None):
         return batched_maximise(func, domain, seed=seed, _fallback=original)
@@ -283,7 +328,13 @@ def accelerate_designers():
         return zero_mean_prediction(gp, x, _fallback=original_zmp)
 
     designers._find_input_repetition_across_levels = patched_rep
+    impl_loo = loo_errors_gp
+
+    def patched_loo(gp, domain, loo_errors_gp=None):
+        return impl_loo(gp, domain, loo_errors_gp, _fallback=original_loo)
+
     designers.compute_zero_mean_prediction = patched_zmp
+    designers.compute_loo_errors_gp = patched_loo
     try:
         yield
     finally:
@@ -291,3 +342,4 @@ def accelerate_designers():
         designers.PEICalculator._add_repulsion_points = original_add
         designers._find_input_repetition_across_levels = original_rep
         designers.compute_zero_mean_prediction = original_zmp
+        designers.compute_loo_errors_gp = original_loo

@@ -156,6 +156,37 @@ def test_multi_level_gp_and_loo(api):
         assert close(a.estimate, b.estimate, rel=1e-7, abs_=1e-8) and close(a.variance, b.variance, rel=1e-7)
 
 
+def test_accelerated_loo_errors_gp_equals_the_unchanged_loop(api):
+    """accel.loo_errors_gp (patched in by accelerate_designers) against the reference's compute_loo_errors_gp on the
+    same B200 GP: the same error training data and, with the same numpy seed, the same fitted errors GP; the same
+    ValueError for a training input outside the domain."""
+    from exauq_toolbox_b200.accel import accelerate_designers
+
+    g = load_golden("fixed_matern_d3_n40.json")
+    data = _data(api, g)
+    domain = api.SimulatorDomain([(0.0, 1.0)] * 3)
+    gp = api.B200GaussianProcess(kernel="Matern52")
+    gp.fit(data, hyperparameters=api.GaussianProcessHyperparameters([0.4, 0.5, 0.6], 1.3, 0.0))
+    np.random.seed(3)
+    plain = api.designers.compute_loo_errors_gp(gp, domain)
+    np.random.seed(3)
+    with accelerate_designers():
+        fast = api.designers.compute_loo_errors_gp(gp, domain)
+    assert len(plain.training_data) == len(fast.training_data) == len(data)
+    for a, b in zip(plain.training_data, fast.training_data):
+        assert a.input == b.input and close(a.output, b.output, rel=1e-12, abs_=1e-14)
+    ha, hb = plain.fit_hyperparameters, fast.fit_hyperparameters
+    assert close(ha.corr_length_scales, hb.corr_length_scales, rel=1e-6) and close(ha.process_var, hb.process_var, rel=1e-6)
+    small = api.SimulatorDomain([(0.0, 0.5)] * 3)
+    for ctx in (False, True):
+        with pytest.raises(ValueError, match="belong to the domain"):
+            if ctx:
+                with accelerate_designers():
+                    api.designers.compute_loo_errors_gp(gp, small)
+            else:
+                api.designers.compute_loo_errors_gp(gp, small)
+
+
 def test_accelerated_multi_level_loo_error_data_equals_the_unchanged_path(api):
     """Inside accelerate_designers() the reference's compute_multi_level_loo_error_data (designers.py:1045-1105) --
     zero-mean predictions through ``kinv @ y`` formed once, cross-level repetition check by a sort -- returns the
