@@ -106,6 +106,53 @@ def test_default_int8_arithmetic_against_oracle(exq, orc, kernel, N, d, ell, nug
         assert e8[q] <= bound, (q, e8[q], e64[q], kappa)
 
 
+def test_batched_evaluation_keeps_ill_conditioned_systems_on_the_top_levels(exq, orc):
+    """Inside a batched log-posterior evaluation every level of the recursion down to the 1024-row nodes runs on 7-digit
+    int8 products (and batches that do not fill the chip too).  At kappa ~ 1e8 that leaves the value 5e-6 from the
+    oracle where FP64 is at 2e-8, so systems whose kappa reaches the guard's widening threshold are re-factored with
+    the int8 kernel on the top levels only.  A batch of three such systems and three benign ones: the guarded values
+    meet the tolerance, the unguarded ones of the ill-conditioned systems do not, and the guard counts its work."""
+    lib = exq._lib
+    kernel, N, d, nug = "SquaredExponential", 2304, 3, 1e-8
+    X, y = orc.synthetic_problem(N, d)
+    rng = np.random.default_rng(12)
+    ells = np.array([0.2, 0.21, 0.19, 0.04, 0.045, 0.05])
+    thetas = np.column_stack([np.tile(-2 * np.log(ells)[:, None], (1, d)) + rng.uniform(-0.02, 0.02, (6, d)),
+                              np.log(1.7) + rng.uniform(-0.1, 0.1, 6)])
+    checked = (0, 3)                                           # one ill-conditioned, one benign system against the oracle
+    want = {b: orc.neg_log_likelihood_grad(X, y, kernel, thetas[b], nug) for b in checked}
+
+    def errors(val, grad):
+        return {b: (abs(val[b] - want[b][0]) / abs(want[b][0]),
+                    float(np.max(np.abs(grad[b] - want[b][1])) / np.max(np.abs(want[b][1])))) for b in checked}
+
+    lib.set_int8_digits(0, 0)                                  # (the digit setting applies to GPs created afterwards)
+    dev = exq.DeviceGP(X, y, kernel)
+    val64, grad64, info64, _ = dev.logpost_batch(thetas, nug)
+    dev.close()
+    e64 = errors(val64, grad64)
+    lib.set_int8_digits(6, 7)
+    lib.set_guard()
+    dev = exq.DeviceGP(X, y, kernel)
+    w0, f0 = lib.guard_counts()
+    val, grad, info, _ = dev.logpost_batch(thetas, nug)
+    w1, f1 = lib.guard_counts()
+    e8 = errors(val, grad)
+    lib.set_guard(1e300, 1e300)                                # guard off: deep 7-digit levels for every system
+    val_off, _, _, _ = dev.logpost_batch(thetas, nug)
+    lib.set_guard()
+    dev.close()
+    assert np.all(info64 == 0) and np.all(info == 0)
+    assert f1 == f0 and w1 - w0 >= 3                           # three systems re-factored on the top levels (+ the LAUUM digits)
+    for b in checked:
+        assert e8[b][0] <= max(1e-9, 4.0 * e64[b][0]), (b, e8[b], e64[b])
+        assert e8[b][1] <= max(1e-7, 4.0 * e64[b][1]), (b, e8[b], e64[b])
+    # the benign systems never left the deep path: identical with the guard off; the ill-conditioned ones moved
+    assert np.array_equal(val_off[3:], val[3:])
+    off0 = abs(val_off[0] - want[0][0]) / abs(want[0][0])
+    assert off0 > 5.0 * max(e8[0][0], 1e-9), (off0, e8[0])
+
+
 def test_refinement_is_what_keeps_the_mean(exq, orc):
     """Without the refinement step the int8 factorisation's predictive mean is ~50 x worse than the FP64 path at
     cond(K) = 4e7 (tools/guard_survey.py); with it the two are level.  Guards the fix, not just the outcome."""
