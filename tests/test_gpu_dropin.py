@@ -234,6 +234,10 @@ def test_accelerated_multi_level_loo_error_data_equals_the_unchanged_path(api):
         except ValueError as e:
             msgs.append(str(e))
     assert len(msgs) == 2 and msgs[0] == msgs[1] and "levels 1, 2" in msgs[0]
+    with accelerate_designers():
+        with pytest.raises(ValueError) as ei:
+            api.designers.compute_multi_level_loo_error_data(ours2)
+    assert str(ei.value) == msgs[0]
 
 
 def test_pei_candidates_matches_reference_peicalculator(api):
