@@ -1893,7 +1893,6 @@ int exq_gp_logpost_batch(exq_gp_t gp, int R, const double* theta_raw, double nug
     } in_logpost_scope;
     Sys& s = gp->batch;
     const int dmax = d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
-    const int nt = Np / 128;
     const double ln2pi = 1.8378770664093453;
     for (int b0 = 0; b0 < R; b0 += Bmax) {
         const int B = std::min(Bmax, R - b0);
