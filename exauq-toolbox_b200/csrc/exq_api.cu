@@ -69,6 +69,7 @@ struct Ctx {
     bool oz_shallow = false;         // set while a system whose kappa reached guard_widen is re-factored with the int8 kernel on
                                      // the top levels only (k >= 1024, chip-filling batches): deeper 7-digit levels cost accuracy as
                                      // conditioning worsens (kappa 1e8: log-posterior 5e-6 from the oracle against 2e-8)
+    int oz_colmax = 1;               // EXQ_OZ_COLMAX=0: separate exponent pass over T instead of column maxima from the epilogue of T's product
     int oz_sched = 1;                // EXQ_OZ_SCHED=0: arithmetic tile walk of the int8 GEMM instead of the balanced work lists
     int grad_fused = 1;              // EXQ_GRAD_FUSED=0: K^-1 stored by LAUUM and contracted by a separate gradient kernel
     int pei_fused = 1;               // EXQ_PEI_FUSED=0: round-1 pipeline (FP64 chunk -> slicer -> per-candidate epilogue)
@@ -248,6 +249,7 @@ struct Sys {
     double* grad = nullptr;                                 // [B][d+2]
     int8_t* oz_planes = nullptr;                            // digit planes of the int8 GEMM operands (lazy)
     int* oz_exp = nullptr;                                  // [2][B][Np] operand row exponents
+    uint32_t* oz_colmax = nullptr;                          // [B][Np] column maxima (high words) of the T products, by global column
     size_t oz_bytes = 0, oz_per_sys = 0;                    // total / per-system bytes of oz_planes
     int64_t sq() const { return (int64_t)Np * Np; }
 };
@@ -256,7 +258,7 @@ void sys_free(Sys& s) {
     cudaFree(s.A); cudaFree(s.Linv); cudaFree(s.W); cudaFree(s.theta); cudaFree(s.tvec);
     cudaFree(s.alpha); cudaFree(s.dinv); cudaFree(s.kvec); cudaFree(s.tpart); cudaFree(s.ldq); cudaFree(s.dstat); cudaFree(s.info);
     cudaFree(s.Xb); cudaFree(s.yb); cudaFree(s.skip); cudaFree(s.gpartial); cudaFree(s.grad);
-    cudaFree(s.oz_planes); cudaFree(s.oz_exp);
+    cudaFree(s.oz_planes); cudaFree(s.oz_exp); cudaFree(s.oz_colmax);
     s = Sys();
 }
 
@@ -273,7 +275,7 @@ size_t sys_bytes(const Sys& s) {
 // a workspace is complete when every buffer its shape calls for exists (a failed cudaMalloc leaves later ones null)
 bool sys_complete(const Sys& s) {
     return s.A && s.Linv && s.theta && s.tvec && s.alpha && s.dinv && s.kvec && s.tpart && s.ldq && s.info && s.grad &&
-           s.dstat && (!s.W || s.gpartial) && (s.oz_bytes == 0 || (s.oz_planes && s.oz_exp)) && (!s.Xb || (s.yb && s.skip));
+           s.dstat && (!s.W || s.gpartial) && (s.oz_bytes == 0 || (s.oz_planes && s.oz_exp && s.oz_colmax)) && (!s.Xb || (s.yb && s.skip));
 }
 
 void sys_release(Sys& s) {
@@ -328,6 +330,7 @@ cudaError_t sys_alloc_buffers(Sys& s, int B, int N, int d, bool need_w, bool own
         s.oz_bytes = s.oz_per_sys * B;
         A(&s.oz_planes, s.oz_bytes);
         A(&s.oz_exp, (size_t)2 * B * s.Np * sizeof(int));
+        A(&s.oz_colmax, (size_t)B * s.Np * sizeof(uint32_t));
     }
     if (own_data) {
         A(&s.Xb, (size_t)B * s.Np * d * sizeof(double));
@@ -454,6 +457,7 @@ struct OzOperand {
     int trans;         // 0: p[row][k], 1: p[k][row]
     int mask;          // oz::MASK_*: which side of the operand's diagonal holds data
     const double* sumsq = nullptr;   // transposed operands: sum_k p[k][row]^2 per system (stride Np) if already known
+    const uint32_t* colmax = nullptr;   // transposed operands: high word of max_k |p[k][row]| per system (stride Np) if already known
 };
 
 // digit planes of both operands (A in the first half of the per-system workspace, B in the second; one operand
@@ -538,7 +542,8 @@ bool sched_get(int M, int N, int K, int B, int krange, int lower_only, SchedEntr
 
 template <int S>
 int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-              int cmode, double fl, bool reuse_a, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
+              int cmode, double fl, bool reuse_a, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1,
+              uint32_t* colmax_out = nullptr) {
     int rc;
     const int64_t ld = s.Np, sq = s.sq();
     int* expA = s.oz_exp;
@@ -548,7 +553,7 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     // reuse_a: the digit planes of A are still in place from the previous product of this node
     ProfMark m = prof_begin(EXQ_PROF_SLICE, 0.0, (double)s.B * K * ((reuse_a ? 0 : M) + (same ? 0 : N)) * (16.0 + S));
     if (!reuse_a) oz::slice_operand<S>(A.p, ld, sq, M, K, s.B, A.trans, A.mask, expA, planesA, g.stream, A.sumsq, s.Np);
-    if (!same) oz::slice_operand<S>(Bm.p, ld, sq, N, K, s.B, Bm.trans, Bm.mask, expB, planesB, g.stream);
+    if (!same) oz::slice_operand<S>(Bm.p, ld, sq, N, K, s.B, Bm.trans, Bm.mask, expB, planesB, g.stream, nullptr, 0, Bm.colmax, s.Np);
     prof_end(m);
     g.launches += (reuse_a ? 0 : (A.trans ? 2 : 1)) + (same ? 0 : (Bm.trans ? 2 : 1)) - 1;
     LAUNCH_CHECK("ozaki operand slicing");
@@ -557,6 +562,10 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
     a.M = M; a.N = N; a.K = K; a.B = s.B; a.krange = krange; a.lower_only = lower_only; a.cmode = cmode;
     a.heavy_last = (krange == KR_LE_J || krange == KR_LE_I) ? 1 : 0;
     if (ga) a.g = *ga;
+    if (colmax_out && cmode == C_STORE) {       // column maxima of C for the product that slices it transposed
+        cudaMemset2DAsync(colmax_out, (size_t)s.Np * sizeof(uint32_t), 0, (size_t)N * sizeof(uint32_t), (size_t)s.B, g.stream);
+        a.colmax = colmax_out; a.colmax_stride = s.Np;
+    }
     SchedEntry se;
     if (sched_get(M, N, K, s.B, krange, lower_only, se)) { a.sched = se.dev; a.n_sched = se.n; a.sched_grid = se.grid; }
     a.sys_slow = 1;   // also for SYRK / LAUUM: at n = 4096 LAUUM streams 12.5 GB per launch otherwise (bench: 240 -> 230 ms)
@@ -582,7 +591,8 @@ int oz_gemm_s(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, in
 }
 
 int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int N, int K, int krange, int lower_only,
-            int cmode, bool reuse_a = false, int digits = 0, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1) {
+            int cmode, bool reuse_a = false, int digits = 0, const oz::GradArgs* ga = nullptr, int grad_kernel_id = -1,
+            uint32_t* colmax_out = nullptr) {
     double fl = 2.0 * M * (double)N * K * s.B;
     if (krange != KR_FULL) fl *= 0.5;
     if (lower_only && krange == KR_FULL) fl *= 0.5;
@@ -591,8 +601,8 @@ int oz_gemm(Sys& s, OzOperand A, OzOperand Bm, bool same, double* C, int M, int 
     if ((digits != 6 && digits != 7) || !oz_planes_fit(s, digits, M, N, K, same))
         return fail(EXQ_ERR_STATE, "int8 GEMM: " + std::to_string(digits) + " digits of a " + std::to_string(M) + " x " +
                                        std::to_string(K) + " operand do not fit the digit-plane workspace");
-    if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id);
-    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id);
+    if (digits == 6) return oz_gemm_s<6>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id, colmax_out);
+    return oz_gemm_s<7>(s, A, Bm, same, C, M, N, K, krange, lower_only, cmode, fl, reuse_a, ga, grad_kernel_id, colmax_out);
 }
 
 // potrf + trtri of the diagonal block [r0, r0+n) of every system in s by ONE launch of fused_factor_kernel
@@ -668,8 +678,10 @@ int factor_rec(Sys& s, int r0, int n) {
     a.A = Li21; a.B = Li11; a.C = A21; a.M = n2; a.N = n1; a.K = n1;
     a.krange = KR_GE_J; a.lower_only = 0; a.cmode = C_STORE;
     if (oz1) {
+        // the column maxima of T (by global column r0 + j: the nodes whose T is alive at the same time own disjoint columns)
+        // are collected by this product's epilogue for (4), which slices T transposed
         if ((rc = oz_gemm(s, {Li21, 0, oz::MASK_NONE}, {Li11, 1, oz::MASK_GE}, false, A21, n2, n1, n1, KR_GE_J, 0, C_STORE,
-                          /*reuse_a=*/oz_syrk)))
+                          /*reuse_a=*/oz_syrk, 0, nullptr, -1, (oz2 && g.oz_colmax) ? s.oz_colmax + r0 : nullptr)))
             return rc;
     } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
@@ -678,7 +690,9 @@ int factor_rec(Sys& s, int r0, int n) {
     a.A = Li22; a.B = A21; a.C = Li21; a.M = n2; a.N = n1; a.K = n2;
     a.krange = KR_LE_I; a.lower_only = 0; a.cmode = C_NEG;
     if (oz2) {
-        if ((rc = oz_gemm(s, {Li22, 0, oz::MASK_LE}, {A21, 1, oz::MASK_NONE}, false, Li21, n2, n1, n2, KR_LE_I, 0, C_NEG)))
+        OzOperand Tt{A21, 1, oz::MASK_NONE};
+        if (oz1 && g.oz_colmax) Tt.colmax = s.oz_colmax + r0;      // T came out of the int8 kernel: its column maxima are known
+        if ((rc = oz_gemm(s, {Li22, 0, oz::MASK_LE}, Tt, false, Li21, n2, n1, n2, KR_LE_I, 0, C_NEG)))
             return rc;
     } else
     if ((rc = launch_gemm<LAYOUT_K, LAYOUT_MN>(a, s.B, EXQ_PROF_GEMM_FACTOR))) return rc;
@@ -1039,6 +1053,7 @@ Sys sys_view(const Sys& s, int b0, int B, int dmax) {
     if (v.oz_planes) {
         v.oz_planes += (size_t)b0 * s.oz_per_sys;
         v.oz_exp += (int64_t)2 * b0 * s.Np;
+        v.oz_colmax += (int64_t)b0 * s.Np;
         v.oz_bytes = s.oz_per_sys * B;
     }
     return v;
@@ -1183,6 +1198,7 @@ int exq_init(int device) {
     if (const char* e = getenv("EXQ_FAST_CORR")) g.fast_corr = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_K")) g.oz_min_k = std::max(128, atoi(e));
     if (const char* e = getenv("EXQ_OZ_SCHED")) g.oz_sched = atoi(e) != 0;
+    if (const char* e = getenv("EXQ_OZ_COLMAX")) g.oz_colmax = atoi(e) != 0;
     if (const char* e = getenv("EXQ_OZAKI_MIN_TILES")) g.oz_min_tiles = atoi(e);
     if (const char* e = getenv("EXQ_PEI_FUSED")) g.pei_fused = atoi(e) != 0;
     if (const char* e = getenv("EXQ_GRAD_FUSED")) g.grad_fused = atoi(e) != 0;

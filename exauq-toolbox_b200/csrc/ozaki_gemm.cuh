@@ -73,6 +73,19 @@ __global__ void __launch_bounds__(256) exponent_from_sumsq_kernel(const double* 
     row_exp[(int64_t)blockIdx.z * n + j] = scale_exponent(bound);
 }
 
+// exponents of the COLUMNS of a product from the column maxima its epilogue left behind (GArgs::colmax: the high word of
+// max |value| per column, collected with redux + atomicMax while the tiles were written): the bound is the largest double
+// with that high word, so the exponent is exact except when max |value| sits within 2^-20 of a rounding boundary of
+// scale_exponent (then one larger: one bit of one column).  Saves the pass over the matrix that operand_exponent_kernel makes.
+__global__ void __launch_bounds__(256) exponent_from_colmax_kernel(const uint32_t* __restrict__ colmax, int64_t stride, int n,
+                                                                   int* __restrict__ row_exp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t hi = colmax[(int64_t)blockIdx.z * stride + j];
+    const double bound = hi ? __hiloint2double((int)hi, (int)0xffffffffu) : 0.0;
+    row_exp[(int64_t)blockIdx.z * n + j] = scale_exponent(bound);
+}
+
 // digits of S planes from a double scaled by 2^(8S - e)
 template <int S>
 __device__ __forceinline__ unsigned long long digits_of(double v, double sc) {
@@ -211,6 +224,8 @@ struct GArgs {
     const uint32_t* sched;   // balanced work list (make_schedule): entry i is the item of CTA i % grid in round i / grid,
     int n_sched;             // packed (system << 20 | I << 10 | J), SCHED_NONE = idle; nullptr: the arithmetic walk above
     int sched_grid;          // CTAs the list was dealt to
+    uint32_t* colmax;        // C_STORE only, may be nullptr: [B][colmax_stride] high words of max |C[:, j]| per column j (atomicMax,
+    int64_t colmax_stride;   // zeroed by the host): the next product slices C transposed and needs its column exponents
 };
 constexpr uint32_t SCHED_NONE = 0xffffffffu;
 
@@ -651,6 +666,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (a.cmode == C_STORE) {
 #pragma unroll
                 for (int c = 0; c < 16; c++) cp[c] = make_double2(z[2 * c], z[2 * c + 1]);
+                if (a.colmax) {
+                    // column maxima of the tile (32 rows of this warp): one redux per column, lane c keeps column c
+                    uint32_t mine = 0u;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const uint32_t m = __reduce_max_sync(0xffffffffu, (uint32_t)__double2hiint(z[c]) & 0x7fffffffu);
+                        if (lane == c) mine = m;
+                    }
+                    atomicMax(a.colmax + (int64_t)b * a.colmax_stride + J * BLK_R + half * 32 + lane, mine);
+                }
             } else if (a.cmode == C_NEG) {
 #pragma unroll
                 for (int c = 0; c < 16; c++) cp[c] = make_double2(-z[2 * c], -z[2 * c + 1]);
@@ -696,11 +721,18 @@ inline cudaError_t set_gemm_attrs() {
 
 // One operand of an int8 GEMM: exponents + digit planes for a batch of B matrices (rows x K each)
 // sumsq != nullptr (transposed operands only): row exponents from the column sums of squares instead of a pass over src
+// colmax != nullptr (transposed operands only): row exponents from the column maxima the producing GEMM collected
 template <int S>
 inline void slice_operand(const double* src, int64_t ld, int64_t stride_sys, int rows, int K, int B, int trans, int mask,
                           int* row_exp, int8_t* planes, cudaStream_t stream, const double* sumsq = nullptr,
-                          int64_t sumsq_stride = 0) {
+                          int64_t sumsq_stride = 0, const uint32_t* colmax = nullptr, int64_t colmax_stride = 0) {
     const int64_t plane_bytes = (int64_t)B * rows * K;
+    if (trans && colmax) {
+        exponent_from_colmax_kernel<<<dim3((rows + 255) / 256, 1, B), 256, 0, stream>>>(colmax, colmax_stride, rows, row_exp);
+        slice_cols_kernel<S><<<dim3(rows / 64, K / 64, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
+                                                                             plane_bytes);
+        return;
+    }
     if (trans && sumsq) {
         exponent_from_sumsq_kernel<<<dim3((rows + 255) / 256, 1, B), 256, 0, stream>>>(sumsq, sumsq_stride, rows, row_exp);
         slice_cols_kernel<S><<<dim3(rows / 64, K / 64, B), 256, 0, stream>>>(src, ld, stride_sys, rows, K, mask, row_exp, planes,
